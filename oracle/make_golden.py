@@ -1,0 +1,245 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+What is produced (all fp32 CPU results of the reference's own classes, imported by
+oracle/ref_import.py; the reference ships no fixtures of its own):
+
+  blocks_small.npz     reference ``hyperTem`` / ``cap`` / ``MLP_RL`` modules on seeded random inputs at
+                       tiny dims, with outputs and every input/parameter gradient for a fixed cotangent.
+  model_<case>.npz     whole ``GPTST_Model`` (state_dict + input + the random draws it consumed) with the
+                       five forward outputs, the probe loss and every parameter gradient, for
+                       eval / pretrain phase 1 / pretrain phase 2 ('all' and 'half', ibd 1 and 2).
+  pems08_ckpt.npz      shipped PEMS08 checkpoint on the first 8 PEMS08 test windows: the input windows,
+                       a strided sample + moments of the eval-mode encoder output, and the pretrain-mode
+                       masked MAE / KL at epoch 1 and 300 (the SURVEY.md §8c numbers).
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+
+from oracle import gptst_oracle as O  # noqa: E402
+from oracle.ref_import import checkpoint_path, load_reference, reference_root  # noqa: E402
+
+GOLD = os.path.join(REPO, "tests", "golden")
+
+
+def small_cfg(**kw):
+    base = dict(num_nodes=9, input_base_dim=1, input_extra_dim=2, hidden_dim=16, output_dim=1, horizon=12, lag=12,
+                embed_dim=4, embed_dim_spa=3, HS=5, HT=6, HT_Tem=4, num_route=2, mode="pretrain", model="TGCN",
+                device="cpu", scaler_zeros=-1.5767, interval=5, week_day=7, mask_ratio=0.25, ada_mask_ratio=0.5,
+                ada_type="all", change_epoch=10, epochs=300)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def run_init(model, seed):
+    torch.manual_seed(seed)
+    for p in model.parameters():  # Run.py:79-85
+        if p.dim() > 1:
+            torch.nn.init.xavier_uniform_(p)
+        else:
+            torch.nn.init.uniform_(p)
+
+
+def npd(t):
+    return t.detach().cpu().numpy()
+
+
+def blocks(ref):
+    torch.manual_seed(123)
+    B, T, N, D, d, ds, H, HT, Ht = 3, 12, 9, 16, 4, 3, 5, 6, 4
+    out = {"dims": np.array([B, T, N, D, d, ds, H, HT, Ht, 2])}
+    # ---- hyperTem
+    m = ref.hyperTem(T, N, D, D, d, Ht)
+    run_init(m, 1)
+    eb = torch.randn(B, T, N, D, requires_grad=True)
+    ne = torch.randn(N, d, requires_grad=True)
+    te = torch.randn(B, T, d, requires_grad=True)
+    y = m(eb, ne, te)
+    g = torch.randn_like(y)
+    y.backward(g)
+    out.update({"ht.eb": npd(eb), "ht.node_emb": npd(ne), "ht.time_eb": npd(te), "ht.adj": npd(m.adj),
+                "ht.weights_pool": npd(m.weights_pool), "ht.bias_pool": npd(m.bias_pool), "ht.out": npd(y),
+                "ht.gout": npd(g), "ht.g.eb": npd(eb.grad), "ht.g.node_emb": npd(ne.grad),
+                "ht.g.time_eb": npd(te.grad), "ht.g.adj": npd(m.adj.grad),
+                "ht.g.weights_pool": npd(m.weights_pool.grad), "ht.g.bias_pool": npd(m.bias_pool.grad)})
+    # ---- cap
+    m = ref.cap(D, N, T, d, ds, H, HT, 2)
+    run_init(m, 2)
+    x = torch.randn(B, T, N, D, requires_grad=True)
+    ne = torch.randn(N, d, requires_grad=True)
+    tes = torch.randn(B, ds, requires_grad=True)
+    teb = torch.randn(B, T, ds, requires_grad=True)
+    y, c, dyn = m(x, ne, tes, teb)
+    g = torch.randn_like(y)
+    y.backward(g)
+    out.update({"cap.x": npd(x), "cap.node_emb": npd(ne), "cap.time_eb_spg": npd(tes), "cap.teb": npd(teb),
+                "cap.ln_p.weight": npd(m.ln_p.weight), "cap.ln_p.bias": npd(m.ln_p.bias), "cap.adj": npd(m.adj),
+                "cap.t_adj": npd(m.t_adj), "cap.weights_spa": npd(m.weights_spa), "cap.bias_spa": npd(m.bias_spa),
+                "cap.out": npd(y), "cap.c": npd(c.squeeze(-1)), "cap.dyn": npd(dyn), "cap.gout": npd(g),
+                "cap.g.x": npd(x.grad), "cap.g.node_emb": npd(ne.grad), "cap.g.time_eb_spg": npd(tes.grad),
+                "cap.g.teb": npd(teb.grad), "cap.g.ln_p.weight": npd(m.ln_p.weight.grad),
+                "cap.g.ln_p.bias": npd(m.ln_p.bias.grad), "cap.g.adj": npd(m.adj.grad), "cap.g.t_adj": npd(m.t_adj.grad),
+                "cap.g.weights_spa": npd(m.weights_spa.grad), "cap.g.bias_spa": npd(m.bias_spa.grad)})
+    # ---- MLP_RL
+    m = ref.MLP_RL(1, H, D, d, "cpu")
+    run_init(m, 3)
+    fl = torch.randn(B, T, N, 1, requires_grad=True)
+    te = torch.randn(B, T, d, requires_grad=True)
+    ne = torch.randn(N, d, requires_grad=True)
+    y = m(fl, te, ne)
+    g = torch.randn_like(y)
+    y.backward(g)
+    out.update({"mlp.flow": npd(fl), "mlp.time_eb": npd(te), "mlp.node_eb": npd(ne), "mlp.out": npd(y), "mlp.gout": npd(g),
+                "mlp.g.flow": npd(fl.grad), "mlp.g.time_eb": npd(te.grad), "mlp.g.node_eb": npd(ne.grad)})
+    for k, p in m.named_parameters():
+        out["mlp.p." + k] = npd(p)
+        out["mlp.g.p." + k] = npd(p.grad)
+    np.savez_compressed(os.path.join(GOLD, "blocks_small.npz"), **out)
+    print("blocks_small.npz", sum(v.size for v in out.values()), "elements")
+
+
+def synth_source(cfg, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, cfg.horizon, cfg.num_nodes, cfg.input_base_dim + 2, generator=g)
+
+
+def model_case(ref, name, cfg, B, epoch, seed):
+    model = ref.GPTST_Model(cfg)
+    run_init(model, seed)
+    src = synth_source(cfg, B, seed + 1)
+    out = {"cfg": np.array([repr(vars(cfg))]), "source": npd(src), "epoch": np.array([epoch if epoch else -1])}
+    for k, v in model.state_dict().items():
+        out["sd." + k] = npd(v)
+    torch.manual_seed(seed + 2)
+    random.seed(seed + 2)
+    res = model(src, src, 1, epoch)
+    if cfg.mode == "pretrain":
+        # replay the draws the reference consumed (same generator algorithm, same order; see Draws.sample)
+        gen = torch.Generator().manual_seed(seed + 2)
+        n = B * cfg.horizon * cfg.num_nodes
+        dr = O.Draws.sample(n * cfg.input_base_dim, n, cfg.HS, epoch > cfg.change_epoch, gen, random.Random(seed + 2))
+        out["draw.u1"] = npd(dr.u1)
+        if dr.u2 is not None:
+            out["draw.u2"] = npd(dr.u2)
+            out["draw.order"] = np.array(dr.class_order)
+        loss = O.synthetic_loss(res, src, epoch, cfg.change_epoch)
+        loss.backward()
+        out["loss"] = npd(loss)
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                out["grad." + k] = npd(p.grad)
+        names = ["flow_out", "flow_decode", "inv_mask", "prob", "hs1"]
+        for nme, t in zip(names, res):
+            out["out." + nme] = npd(t)
+    else:
+        out["out.enc"] = npd(res[0])
+    np.savez_compressed(os.path.join(GOLD, f"model_{name}.npz"), **out)
+    print(f"model_{name}.npz", sum(v.size for v in out.values()), "elements")
+
+
+def pems08_windows(root):
+    """First 8 windows of the PEMS08 test split, through the reference's own lib/ pipeline."""
+    npz = None
+    for r in (root, os.path.join(REPO, "baseline", "_ref")):
+        p = os.path.join(r, "data", "PEMS08", "PEMS08.npz")
+        if os.path.isfile(p):
+            npz = p
+            break
+    if npz is None:
+        return None
+    sys.path.insert(0, root)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(os.path.dirname(os.path.dirname(npz)), "..", "model"))
+    try:
+        from lib.dataloader import get_dataloader
+        a = types.SimpleNamespace(dataset="PEMS08", val_ratio=0.2, test_ratio=0.2, lag=12, horizon=12, input_base_dim=1,
+                                  column_wise=False, batch_size=8)
+        _, _, te, sc, _, _, _ = get_dataloader(a, normalizer="std", tod=False, dow=False, weather=False, single=False)
+        x = next(iter(te))[0][:8, ..., :3].cpu()
+        return x, float(sc.mean), float(sc.std), a.interval, a.week_day
+    finally:
+        os.chdir(cwd)
+
+
+def pems08(ref, root):
+    ck = checkpoint_path("PEMS08")
+    got = pems08_windows(root)
+    if ck is None or got is None:
+        print("pems08: checkpoint or dataset missing, skipped")
+        return
+    x, mean, std, interval, week_day = got
+    zeros = (0 - mean) / std
+    sd = torch.load(ck, map_location="cpu")
+    out = {"x": npd(x), "mean": np.array([mean]), "std": np.array([std]), "scaler_zeros": np.array([zeros])}
+
+    def cfg(mode):
+        return types.SimpleNamespace(num_nodes=170, input_base_dim=1, input_extra_dim=2, hidden_dim=64, output_dim=1,
+                                     horizon=12, lag=12, embed_dim=16, embed_dim_spa=4, HS=10, HT=16, HT_Tem=8, num_route=2,
+                                     mode=mode, model="STGCN", device="cpu", scaler_zeros=zeros, interval=interval,
+                                     week_day=week_day, mask_ratio=0.25, ada_mask_ratio=0.5, ada_type="all",
+                                     change_epoch=10, epochs=300)
+
+    m = ref.GPTST_Model(cfg("eval"))
+    print(m.load_state_dict(sd, strict=True))
+    with torch.no_grad():
+        o = m(x, x)[0]
+    out["eval.sample"] = npd(o[:, :, ::10, ::4])
+    out["eval.moments"] = np.array([o.mean().item(), o.abs().mean().item(), o.std().item(), o.abs().max().item()])
+    out["eval.first6"] = npd(o[0, 0, 0, :6])
+    out["eval.last4"] = npd(o[7, 11, 169, -4:])
+    print("eval moments", out["eval.moments"], out["eval.first6"])
+    m = ref.GPTST_Model(cfg("pretrain"))
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    for ep in (1, 300):
+        torch.manual_seed(12)
+        random.seed(12)
+        with torch.no_grad():
+            fo, _, inv, prob, hs = m(x, x, None, ep)
+        gen = torch.Generator().manual_seed(12)
+        n = x.shape[0] * 12 * 170
+        dr = O.Draws.sample(n, n, 10, ep > 10, gen, random.Random(12))
+        out[f"pre{ep}.u1"] = npd(dr.u1)
+        if dr.u2 is not None:
+            out[f"pre{ep}.u2"] = npd(dr.u2)
+            out[f"pre{ep}.order"] = np.array(dr.class_order)
+        msk = inv.bool()
+        mae = ((fo - x[..., :1]) * std).abs()[msk].mean().item()
+        kl = torch.nn.KLDivLoss(reduction="sum")(prob.log(), hs).item()
+        out[f"pre{ep}.stats"] = np.array([mae, int(msk.sum()), kl])
+        out[f"pre{ep}.inv_mask_packed"] = np.packbits(npd(inv).astype(np.uint8).reshape(-1))
+        out[f"pre{ep}.flow_out_sample"] = npd(fo[:, :, ::5, 0])
+        print(f"pretrain epoch {ep}: masked MAE {mae:.5f} cells {int(msk.sum())} KL {kl:.4f}")
+    np.savez_compressed(os.path.join(GOLD, "pems08_ckpt.npz"), **out)
+    print("pems08_ckpt.npz", sum(v.size for v in out.values()), "elements")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    root = reference_root()
+    ref = load_reference("cpu", root)
+    torch.set_num_threads(4)
+    blocks(ref)
+    model_case(ref, "eval", small_cfg(mode="eval"), 3, None, 10)
+    model_case(ref, "pre_phase1", small_cfg(), 3, 1, 20)
+    model_case(ref, "pre_phase2_all", small_cfg(), 3, 200, 30)
+    model_case(ref, "pre_phase2_half", small_cfg(ada_type="half"), 3, 299, 40)
+    model_case(ref, "pre_phase1_ibd2", small_cfg(input_base_dim=2), 2, 5, 50)
+    model_case(ref, "pre_phase2_ibd2", small_cfg(input_base_dim=2), 2, 120, 60)
+    pems08(ref, root)
+
+
+if __name__ == "__main__":
+    main()
