@@ -1,0 +1,65 @@
+"""ctypes binding of libgptst_b200.so (the C ABI of include/gptst_b200.h).  Fails loudly when absent."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgptst_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+_f = C.c_void_p  # device pointers are passed as integers
+_i, _l = C.c_int, C.c_long
+
+# name -> (restype, argtypes); must list every symbol declared in include/gptst_b200.h
+SIGNATURES = {
+    "gptst_gproj_fwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _f]),
+    "gptst_gproj_splits": (_i, [_i, _i, _i]),
+    "gptst_gproj_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _i, _f]),
+    "gptst_tmix": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_tmix_dM_splits": (_i, [_i, _i]),
+    "gptst_tmix_dM": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_route_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_hop_fwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_recon": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_dv_dcr": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_route_bwd_parts": (_i, [_i, _i, _i, _i, _i]),
+    "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_version": (C.c_char_p, []),
+}
+
+
+class GptstLibraryError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library.  No fallback: raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise GptstLibraryError(
+                    f"{LIB_PATH} not found: build it with `python gpt-st_b200/build.py` "
+                    "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for this path.")
+            handle = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(handle, name)  # AttributeError if the symbol is missing
+                fn.restype, fn.argtypes = res, args
+            _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc == -1:
+        raise GptstLibraryError(f"{what}: NULL / empty argument")
+    if rc == -2:
+        raise GptstLibraryError(f"{what}: unsupported shape (D in {{64,128}}, T == 12, H <= 16, prec in {{1,3}})")
+    raise GptstLibraryError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,220 @@
+"""Autograd functions over the C ABI (include/gptst_b200.h) for the three heavy blocks of
+GPT-ST's pre-training model: ``hypertem`` (GPTST.py:154-163), ``cap`` (GPTST.py:100-141) and the
+adaptive projections of ``MLP_RL`` (GPTST.py:24-32).
+
+Only the (B,T,N,D)-sized work runs here; the parameter-sized contractions that feed it (node/time
+adaptive weight tables, incidence logits) are produced by the caller (GPTST.py of this package).
+CUDA tensors only -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+PREC_TF32 = 1
+PREC_3XTF32 = 3
+
+
+def default_precision() -> int:
+    """3xTF32 (fp32-faithful) unless GPTST_B200_PRECISION=tf32 asks for single-pass TF32."""
+    v = os.environ.get("GPTST_B200_PRECISION", "3xtf32").lower()
+    if v in ("tf32", "1"):
+        return PREC_TF32
+    if v in ("3xtf32", "3", "fp32"):
+        return PREC_3XTF32
+    raise ValueError(f"GPTST_B200_PRECISION={v!r}: expected 'tf32' or '3xtf32'")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"gptst_b200 ops are fp32, got {t.dtype}")
+        if not t.is_contiguous():
+            raise RuntimeError("gptst_b200 ops need contiguous tensors")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------
+# thin kernel wrappers (no autograd)
+# ---------------------------------------------------------------------------------------------------
+def gproj_fwd(X, W, bias, res, *, node_grouped: bool, act: bool, prec: int):
+    """X (B,T,N,D).  time-grouped: W (B*T,D,D)/(B,T,D,D); node-grouped: W (N,D,D)."""
+    B, T, N, D = X.shape
+    _chk(X, W)
+    Y = torch.empty_like(X)
+    if node_grouped:
+        G, R, gs, rs = N, B * T, D, N * D
+    else:
+        G, R, gs, rs = B * T, N, N * D, D
+    rc = _lib.lib().gptst_gproj_fwd(_p(X), _p(W), _p(bias), _p(res), _p(Y), G, R, gs, rs, D, int(act), prec, _stream())
+    _lib.check(rc, "gptst_gproj_fwd")
+    return Y
+
+
+def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dres: bool):
+    B, T, N, D = X.shape
+    _chk(dY, X, W)
+    if node_grouped:
+        G, R, gs, rs = N, B * T, D, N * D
+    else:
+        G, R, gs, rs = B * T, N, N * D, D
+    L = _lib.lib()
+    splits = L.gptst_gproj_splits(G, R, D)
+    dX = torch.empty_like(X)
+    dWp = torch.empty((splits, G, D, D), device=X.device, dtype=torch.float32)
+    dbp = torch.empty((splits, G, D), device=X.device, dtype=torch.float32)
+    dres = torch.empty_like(X) if want_dres else None
+    rc = L.gptst_gproj_bwd(_p(dY), _p(Y) if act else None, _p(X), _p(W), _p(dX), _p(dWp), _p(dbp), _p(dres), G, R, gs, rs,
+                           D, int(act), prec, splits, _stream())
+    _lib.check(rc, "gptst_gproj_bwd")
+    dW = dWp[0] if splits == 1 else dWp.sum(0)
+    db = dbp[0] if splits == 1 else dbp.sum(0)
+    return dX, dW, db, dres
+
+
+def tmix(x, M, out=None, *, transpose=False, accumulate=False):
+    B, T, N, D = x.shape
+    _chk(x, M)
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.lib().gptst_tmix(_p(x), _p(M), _p(out), B, T, N, D, int(transpose), int(accumulate), _stream())
+    _lib.check(rc, "gptst_tmix")
+    return out
+
+
+def tmix_dM(dy, x):
+    B, T, N, D = x.shape
+    _chk(dy, x)
+    L = _lib.lib()
+    splits = L.gptst_tmix_dM_splits(B, N)
+    part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
+    rc = L.gptst_tmix_dM(_p(dy), _p(x), _p(part), B, T, N, D, splits, _stream())
+    _lib.check(rc, "gptst_tmix_dM")
+    return part[0] if splits == 1 else part.sum(0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# hyperTem core:  out = LReLU( (M_n o eb) . W_bt + bias_bt + eb )
+# ---------------------------------------------------------------------------------------------------
+class _HyperTemCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eb, Mn, W, bias, prec):
+        eb, Mn, W, bias = eb.contiguous(), Mn.contiguous(), W.contiguous(), bias.contiguous()
+        ret = tmix(eb, Mn)
+        out = gproj_fwd(ret, W, bias, eb, node_grouped=False, act=True, prec=prec)
+        ctx.save_for_backward(eb, Mn, W, ret, out)
+        ctx.prec = prec
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eb, Mn, W, ret, out = ctx.saved_tensors
+        dout = dout.contiguous()
+        dret, dW, db, deb = gproj_bwd(dout, out, ret, W, node_grouped=False, act=True, prec=ctx.prec, want_dres=True)
+        tmix(dret, Mn, deb, transpose=True, accumulate=True)
+        dM = tmix_dM(dret, eb)
+        B, T, N, D = eb.shape
+        return deb, dM, dW.view(B, T, D, D), db.view(B, T, D), None
+
+
+def hypertem_core(eb, Mn, W, bias, prec=None):
+    """eb (B,T,N,D); Mn (N,T,T) = A_n^T A_n; W (B,T,D,D); bias (B,T,D)."""
+    return _HyperTemCore.apply(eb, Mn, W, bias, default_precision() if prec is None else prec)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cap core
+# ---------------------------------------------------------------------------------------------------
+class _CapCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec):
+        x, Wp, bp, dadj, dyn, Wn, bn = (t.contiguous() for t in (x, Wp, bp, dadj, dyn, Wn, bn))
+        _chk(x, Wp, bp, dadj, dyn, Wn, bn)
+        B, T, N, D = x.shape
+        H, HT = dadj.shape[2], dyn.shape[1]
+        L = _lib.lib()
+        st = _stream()
+        c = torch.empty((B, T, H, N), device=x.device, dtype=torch.float32)
+        s = torch.empty((B, T, H, D), device=x.device, dtype=torch.float32)
+        _lib.check(L.gptst_cap_route_fwd(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), B, T, N, D, H, int(num_route),
+                                         prec, st), "gptst_cap_route_fwd")
+        v = torch.empty_like(s)
+        _lib.check(L.gptst_cap_hop_fwd(_p(s), _p(dyn), _p(v), B, T, D, H, HT, st), "gptst_cap_hop_fwd")
+        recon = torch.empty_like(x)
+        _lib.check(L.gptst_cap_recon(_p(c), _p(v), _p(recon), B, T, N, D, H, st), "gptst_cap_recon")
+        out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
+        ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out)
+        ctx.prec = prec
+        ctx.mark_non_differentiable(c)
+        return out, c
+
+    @staticmethod
+    def backward(ctx, dout, _dc):
+        x, Wp, bp, dyn, Wn, c, s, v, recon, out = ctx.saved_tensors
+        B, T, N, D = x.shape
+        H, HT = c.shape[2], dyn.shape[1]
+        L = _lib.lib()
+        st = _stream()
+        dout = dout.contiguous()
+        drecon, dWn, dbn, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True)
+        dv = torch.empty_like(s)
+        dcr = torch.empty_like(c)
+        _lib.check(L.gptst_cap_dv_dcr(_p(c), _p(v), _p(drecon), _p(dv), _p(dcr), B, T, N, D, H, st), "gptst_cap_dv_dcr")
+        ds = torch.empty_like(s)
+        ddyn = torch.empty_like(dyn)
+        _lib.check(L.gptst_cap_hop_bwd(_p(s), _p(dyn), _p(dv), _p(ds), _p(ddyn), B, T, D, H, HT, st), "gptst_cap_hop_bwd")
+        parts = L.gptst_cap_route_bwd_parts(B, T, N, D, H)
+        dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)
+        dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
+        ddadj = torch.empty_like(c)
+        _lib.check(L.gptst_cap_route_bwd(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dx), _p(ddadj), _p(dWp_part),
+                                         _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
+        return dx, dWp_part.sum(0), dbp_part.sum(0), ddadj, ddyn, dWn, dbn, None, None
+
+
+def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None):
+    """x (B,T,N,D); Wp (D,D) [out,in]; dadj (B,T,H,N); dyn (B,HT,T*H); Wn (N,D,D); bn (N,D).
+    Returns (out (B,T,N,D), c (B,T,H,N) non-differentiable)."""
+    return _CapCore.apply(x, Wp, bp, dadj, dyn, Wn, bn, num_route, default_precision() if prec is None else prec)
+
+
+# ---------------------------------------------------------------------------------------------------
+# adaptive projection (MLP_RL stages):  y = LReLU(x . W_g + b_g)
+# ---------------------------------------------------------------------------------------------------
+class _AdaptiveProj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, b, node_grouped, prec):
+        x, W, b = x.contiguous(), W.contiguous(), b.contiguous()
+        y = gproj_fwd(x, W, b, None, node_grouped=node_grouped, act=True, prec=prec)
+        ctx.save_for_backward(x, W, y)
+        ctx.node_grouped, ctx.prec = node_grouped, prec
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dX, dW, db, _ = gproj_bwd(dy.contiguous(), y, x, W, node_grouped=ctx.node_grouped, act=True, prec=ctx.prec,
+                                  want_dres=False)
+        return dX, dW.view_as(W), db.view(W.shape[:-2] + (W.shape[-1],)), None, None
+
+
+def node_adaptive_proj(x, Wn, bn, prec=None):
+    """y[b,t,n,:] = LReLU(x[b,t,n,:] . Wn[n] + bn[n])      GPTST.py:24-27"""
+    return _AdaptiveProj.apply(x, Wn, bn, True, default_precision() if prec is None else prec)
+
+
+def time_adaptive_proj(x, Wt, bt, prec=None):
+    """y[b,t,n,:] = LReLU(x[b,t,n,:] . Wt[b,t] + bt[b,t])  GPTST.py:29-32"""
+    return _AdaptiveProj.apply(x, Wt, bt, False, default_precision() if prec is None else prec)

@@ -1,0 +1,82 @@
+/* gptst_b200.h -- C ABI of the B200-native GPT-ST pre-training hot path (libgptst_b200.so).
+ *
+ * Every entry point:
+ *   - takes raw DEVICE pointers to contiguous fp32 buffers (no torch types), plain int sizes and a
+ *     cudaStream_t passed as void*;
+ *   - is stream-ordered and asynchronous: no allocation, no host synchronisation, no global state, so the
+ *     calls can be captured into a CUDA graph;
+ *   - returns 0 on success, a positive cudaError_t on a CUDA failure, -1 for a NULL/empty argument and
+ *     -2 for an unsupported shape (D must be 64 or 128, T == 12, H <= 16, prec in {1,3}).
+ *
+ * The reference (HKUDS/GPT-ST) has no FFI: the path is pure PyTorch.  Each function below replaces the
+ * cited lines of /root/reference/model/Pretrain_model/GPTST.py; INTEGRATION.md shows the ctypes binding.
+ *
+ * Layout conventions (all row-major, last index fastest):
+ *   activation  x, eb, out ...  (B, T, N, D)          slab = one (b,t) block of N x D
+ *   c, dadj, dcr, ddadj         (B, T, H, N)          hyperedge-major incidence per slab
+ *   s, v, dv, ds                (B, T, H, D)
+ *   dyn, ddyn                   (B, HT, T*H)
+ * prec: 1 = TF32 tensor-core operands, 3 = 3xTF32 split (fp32-faithful, default of the Python layer).
+ */
+#ifndef GPTST_B200_H
+#define GPTST_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- grouped D x D projection with per-group weights -------------------------------------------------
+ * Y[g][r][:] = act( X[g][r][:] . W[g] + bias[g] (+ Res[g][r][:]) ),  element (g,r,j) at
+ * base + g*group_stride + r*row_stride + j.  W (G,D,D) is [in][out]; bias (G,D) may be NULL; Res may be NULL.
+ * act: 0 = identity, 1 = LeakyReLU(0.01).
+ *   time-adaptive projection  GPTST.py:160-163 (hyperTem), :29-32 (MLP_RL):  G=B*T, R=N,   gs=N*D, rs=D
+ *   node-adaptive projection  GPTST.py:137-141 (cap),      :24-27 (MLP_RL):  G=N,   R=B*T, gs=D,   rs=N*D   */
+int gptst_gproj_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R,
+                    long group_stride, long row_stride, int D, int act, int prec, void* stream);
+/* Backward of the above.  dy = dY * act'(Y)  (Y may be NULL when act == 0).
+ *   dX = dy . W^T ;  dW_part[s][g] = partial sum_r X^T dy ;  dbias_part[s][g] = partial sum_r dy ;  dRes = dy (may be NULL)
+ * dW_part is (splits, G, D, D), dbias_part (splits, G, D); the caller sums over `splits`
+ * (splits = gptst_gproj_splits(G, R, D) row-range CTAs per group keep the reduction deterministic).          */
+int gptst_gproj_splits(int G, int R, int D);
+int gptst_gproj_bwd(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dW_part,
+                    float* dbias_part, float* dRes, int G, int R, long group_stride, long row_stride, int D, int act,
+                    int prec, int splits, void* stream);
+
+/* ---- temporal hypergraph two-hop of hyperTem, GPTST.py:156-158, as a per-node T x T mix ---------------
+ * y[b,t,n,:] (+)= sum_t' M[n][t][t'] x[b,t',n,:]   (transpose != 0 uses M[n][t'][t]); M is (N,T,T).           */
+int gptst_tmix(const float* x, const float* M, float* y, int B, int T, int N, int D, int transpose, int accumulate,
+               void* stream);
+/* dM_part[s][n][t][t'] = partial over batch split s of sum_{b,j} dy[b,t,n,j] x[b,t',n,j]                       */
+int gptst_tmix_dM_splits(int B, int N);
+int gptst_tmix_dM(const float* dy, const float* x, float* dM_part, int B, int T, int N, int D, int splits, void* stream);
+
+/* ---- cap: intra-cluster routing, GPTST.py:102-123 ----------------------------------------------------
+ * P = squash(x Wp^T + bp); R routing iterations on (P, dadj); c = softmax_H(b + dadj) -> c (B,T,H,N); s = c P.
+ * One thread-block cluster per (b,t) slab; the cluster size is chosen so the slab's P tile stays in shared memory. */
+int gptst_cap_route_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int B,
+                        int T, int N, int D, int H, int R, int prec, void* stream);
+/* ---- cap: inter-cluster hop over k=(t,h) per sample, GPTST.py:125-134:  v = squash(LReLU(dyn^T LReLU(dyn (s+tau))) + s) */
+int gptst_cap_hop_fwd(const float* s, const float* dyn, float* v, int B, int T, int D, int H, int HT, void* stream);
+/* ---- cap: hyperedge -> node reconstruction, GPTST.py:135:  recon[b,t,n,:] = sum_h c[b,t,h,n] v[b,t,h,:]      */
+int gptst_cap_recon(const float* c, const float* v, float* recon, int B, int T, int N, int D, int H, void* stream);
+/* ---- cap backward pieces ------------------------------------------------------
+ * dv = c drecon, dcr = v drecon^T                                                                            */
+int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int B, int T, int N,
+                     int D, int H, void* stream);
+/* dv -> ds (B,T,H,D) and ddyn (B,HT,T*H)                                                                      */
+int gptst_cap_hop_bwd(const float* s, const float* dyn, const float* dv, float* ds, float* ddyn, int B, int T, int D,
+                      int H, int HT, void* stream);
+/* dx_io holds dy = dOut*act'(out) on entry and dy + dZ Wp on exit; ddadj (B,T,H,N);
+ * dWp_part (parts,D,D) [out][in], dbp_part (parts,D) with parts = gptst_cap_route_bwd_parts(...)              */
+int gptst_cap_route_bwd_parts(int B, int T, int N, int D, int H);
+int gptst_cap_route_bwd(const float* x, const float* Wp, const float* bp, const float* c, const float* ds,
+                        const float* dcr, float* dx_io, float* ddadj, float* dWp_part, float* dbp_part, int B, int T,
+                        int N, int D, int H, int prec, void* stream);
+
+/* library identification: "gptst_b200 <version> sm_100a" */
+const char* gptst_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPTST_B200_H */
