@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- pre-training samples/s of the GPT-ST hot path on B200 (BASELINE.json metric) + roofline of the
+fused hypergraph / adaptive-GCN block.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full pre-training step on one synthetic batch: zero_grad, GPTST_Model forward (mask scoring,
+masking, encoder + decoder STHCN), loss, backward, (N>1: one flat-gradient NCCL all-reduce),
+clip_grad_norm_(5), Adam(lr 3e-3) -- the step of the reference trainer (BasicTrainer.py:72-103) on the synthetic
+inputs of the driver's GPU probe.  Workload = BASELINE.json configs[1]: PEMS08 geometry,
+batch 64 per GPU, N=170, T=12, D=64, epoch argument 200 (adaptive-mask + KL phase, 290 of the 300 epochs).
+Weak scaling: every rank keeps batch 64; `value` = world * 64 * K / max-over-ranks device time.
+
+--impl reference times the reference's own CPU PyTorch implementation of the same step on the host cores
+(rank 0 only).  See DESIGN.md section "Measurement" for every field of the JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+T_STEPS = 12
+WORKLOADS = {
+    # name: (N, D, per-GPU batch)
+    "pems08": (170, 64, 64),
+    "metr_la": (207, 64, 64),
+    "synthetic2048": (2048, 128, 16),
+}
+
+
+def make_cfg(N, D, device):
+    return types.SimpleNamespace(num_nodes=N, input_base_dim=1, input_extra_dim=2, hidden_dim=D, output_dim=1, horizon=12,
+                                 lag=12, embed_dim=16, embed_dim_spa=4, HS=10, HT=16, HT_Tem=8, num_route=2, mode="pretrain",
+                                 model="TGCN", device=device, scaler_zeros=-1.5767, interval=5, week_day=7, mask_ratio=0.25,
+                                 ada_mask_ratio=0.5, ada_type="all", change_epoch=10, epochs=300)
+
+
+def run_init(model, seed=0):
+    torch.manual_seed(seed)
+    for p in model.parameters():  # reference Run.py:79-85
+        if p.dim() > 1:
+            torch.nn.init.xavier_uniform_(p)
+        else:
+            torch.nn.init.uniform_(p)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own PyTorch code on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_stepper(N, D, B, epoch):
+    """Returns (step_fn, kind).  kind 'reference' = unmodified reference module from the driver-provided install
+    (baseline/_ref) with the six 'cuda:0' literals rewritten to 'cpu'; 'port' = the oracle restatement."""
+    from oracle import gptst_oracle as O
+    from oracle.ref_import import load_reference, reference_root
+    cfg = make_cfg(N, D, "cpu")
+    x = torch.randn(B, T_STEPS, N, 3, generator=torch.Generator().manual_seed(0))
+    kl = torch.nn.KLDivLoss(reduction="sum")
+    root = reference_root()
+    if root is not None:
+        ref = load_reference("cpu", root)
+        torch.manual_seed(0)
+        m = ref.GPTST_Model(cfg)
+        run_init(m, 0)
+        opt = torch.optim.Adam(m.parameters(), lr=3e-3, eps=1e-8)
+
+        def step():
+            opt.zero_grad()
+            o, _, mask, prob, hs = m(x, x, 1, epoch)
+            loss = ((o - x[..., :1]) * mask).abs().mean()
+            if epoch > 10:
+                loss = loss + 0.1 * kl(prob.log(), hs)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+            opt.step()
+            return float(loss.detach())
+        return step, "reference"
+    import random
+    P = {k: v.requires_grad_() for k, v in O.init_params(cfg, 0).items()}
+    opt = torch.optim.Adam(list(P.values()), lr=3e-3, eps=1e-8)
+    gen, pyr = torch.Generator().manual_seed(0), random.Random(0)
+
+    def step():
+        opt.zero_grad()
+        n = B * T_STEPS * N
+        dr = O.Draws.sample(n, n, cfg.HS, epoch > cfg.change_epoch, gen, pyr)
+        outs = O.model_forward(P, cfg, x, epoch, dr)
+        loss = O.synthetic_loss(outs, x, epoch)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([p for p in P.values() if p.grad is not None], 5)
+        opt.step()
+        return float(loss.detach())
+    return step, "port"
+
+
+def time_cpu(step, steps, warmup, budget_s=None):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    return (time.perf_counter() - t0) / done, done
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    N, D, B = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, kind = cpu_reference_stepper(N, D, B, args.epoch)
+    sec, done = time_cpu(step, args.steps, args.warmup)
+    value = B / sec
+    line = {
+        "impl": "reference", "metric": "pretrain samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, B, 1, args.epoch) | {"device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": f"{done} full training steps at batch {B} after {args.warmup} warm-up, all {cores} host threads"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(name, B, world, epoch):
+    N, D, _ = WORKLOADS[name]
+    return {"workload": f"{name}: GPT-ST pretrain step, N={N}, T=12, D={D}, batch {B}/GPU (BASELINE.json configs[1] geometry)"
+            if name == "pems08" else f"{name}: GPT-ST pretrain step, N={N}, T=12, D={D}, batch {B}/GPU",
+            "global_batch": B * world, "per_gpu_batch": B, "num_nodes": N, "hidden_dim": D, "epoch_arg": epoch,
+            "mask_phase": "adaptive+KL" if epoch > 10 else "random", "optimizer": "Adam lr 3e-3, clip_grad_norm 5",
+            "parallelism": f"dp{world}"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def cap_forward_roofline(N, D, B, iters=20):
+    """cap forward (GPTST.py:100-141) timed alone with CUDA events on the launching stream, on rotating buffer
+    sets larger than L2 so every launch reads x from HBM.  Algorithmic bytes: 4*B*T*N*(2D+H)."""
+    from gptst_b200 import ops
+    H, HT, d, ds, T = 10, 16, 16, 4, T_STEPS
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    nset = max(3, int(400e6 // (2 * 4 * B * T * N * D)) + 1)
+    xs = [torch.randn(B, T, N, D, device=dev, generator=g) for _ in range(nset)]
+    Wp = torch.randn(D, D, device=dev, generator=g) * D ** -0.5
+    bp = torch.rand(D, device=dev, generator=g)
+    dadj = torch.randn(B, T, H, N, device=dev, generator=g)
+    dyn = torch.randn(B, HT, T * H, device=dev, generator=g) * 0.3
+    Wn = torch.randn(N, D, D, device=dev, generator=g) * D ** -0.5
+    bn = torch.rand(N, D, device=dev, generator=g)
+    prec = ops.default_precision()
+    times = []
+    with torch.no_grad():
+        for i in range(3 + iters):
+            x = xs[i % nset]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.cap_core(x, Wp, bp, dadj, dyn, Wn, bn, 2, prec)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    algo = 4 * B * T * N * (2 * D + H)
+    return algo, ms
+
+
+def hypertem_forward_time(N, D, B, iters=20):
+    from gptst_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    nset = max(3, int(400e6 // (2 * 4 * B * T_STEPS * N * D)) + 1)
+    xs = [torch.randn(B, T_STEPS, N, D, device=dev, generator=g) for _ in range(nset)]
+    Mn = torch.randn(N, 12, 12, device=dev, generator=g) * 0.2
+    W = torch.randn(B, 12, D, D, device=dev, generator=g) * D ** -0.5
+    b = torch.rand(B, 12, D, device=dev, generator=g)
+    prec = ops.default_precision()
+    times = []
+    with torch.no_grad():
+        for i in range(3 + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.hypertem_core(xs[i % nset], Mn, W, b, prec)
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1))
+    return 8 * B * T_STEPS * N * D, statistics.median(times)
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from gptst_b200 import dp, ops
+    from gptst_b200.GPTST import GPTST_Model
+    from gptst_b200.losses import probe_loss
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: the product path needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    rank, local, world = dp.init_from_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    N, D, B = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    epoch = args.epoch
+    cfg = make_cfg(N, D, "cuda")
+    model = GPTST_Model(cfg).to(dev)
+    run_init(model, 0)
+    dp.broadcast_parameters(model)
+    reducer = dp.FlatGradAllReduce(model.parameters()).attach()
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3, eps=1e-8)
+
+    # synthetic inputs (standard normal); distinct per rank
+    gcpu = torch.Generator().manual_seed(100 + rank)
+    nbuf = 4
+    host = [torch.randn(B, T_STEPS, N, 3, generator=gcpu).pin_memory() for _ in range(nbuf)]
+    resident = [h.to(dev) for h in host]
+    staging = torch.empty_like(resident[0])
+
+    def train_step(x):
+        opt.zero_grad(set_to_none=True)
+        outs = model(x, x, 1, epoch)
+        loss = probe_loss(outs, x, epoch, cfg.change_epoch)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        barrier()
+        l0 = ops.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(nsteps):
+            if e2e:
+                staging.copy_(host[i % nbuf], non_blocking=True)       # H2D of this step's batch from pinned memory
+                last = float(train_step(staging))                      # D2H read of the loss
+            else:
+                last = train_step(resident[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ops.launch_count() - l0, float(last)
+
+    random_seed = 1234 + rank
+    import random
+    random.seed(random_seed)
+    torch.manual_seed(random_seed)
+    for i in range(max(3, args.warmup)):
+        train_step(resident[i % nbuf])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, last_loss = timed(args.steps, e2e=False)
+    ms_e2e, _, _ = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * B * args.steps / (ms * 1e-3)
+    value_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        algo, cap_ms = cap_forward_roofline(N, D, B)
+        ht_algo, ht_ms = hypertem_forward_time(N, D, B)
+        achieved = algo / (cap_ms * 1e-3) / 1e9
+        step_bytes = (60 * 4 * B * T_STEPS * N * D) + (8 * 4 * B * T_STEPS * N * 10)
+        line = {
+            "metric": "pretrain samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core contractions, fp32 accumulate)"
+            if ops.default_precision() == 3 else "tf32 operands, fp32 accumulate",
+            "data": "synthetic", "config": workload_config(args.workload, B, world, epoch) | {
+                "l2": "no flush between steps: one step touches ~2 GB of activations/gradients >> 126 MB L2; "
+                      "kernel roofline timed on rotating buffer sets > L2"},
+            "e2e": {"value": value_e2e, "unit": "samples/s", "h2d_bytes_per_step": staging.numel() * 4 * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + cap_hop_fwd + cap_recon + gproj_fwd), "
+                         "the hypergraph + node-adaptive GCN block", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
+            "roofline_hypertem_fwd": {"achieved": ht_algo / (ht_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ht_ms,
+                                      "algorithmic_bytes": ht_algo, "frac": ht_algo / (ht_ms * 1e-3) / 1e9 / peak},
+            "step_roofline": {"algorithmic_bytes": step_bytes, "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "last_loss": last_loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            step, kind = cpu_reference_stepper(N, D, B, epoch)
+            sec, done = time_cpu(step, 12, 1, budget_s=15.0)
+            line["cpu_baseline"] = {"value": B / sec, "unit": "samples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{done} full training steps at batch {B} (after 1 warm-up) on {cores} host threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pems08", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--epoch", type=int, default=200, help="epoch argument passed to the model (mask phase)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

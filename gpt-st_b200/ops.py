@@ -28,8 +28,22 @@ def default_precision() -> int:
     raise ValueError(f"GPTST_B200_PRECISION={v!r}: expected 'tf32' or '3xtf32'")
 
 
+_launches = 0  # kernels of libgptst_b200.so launched by this process (every C-ABI call launches exactly one)
+
+
+def launch_count() -> int:
+    return _launches
+
+
 def _stream() -> int:
+    global _launches
+    _launches += 1
     return torch.cuda.current_stream().cuda_stream
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
 
 
 def _chk(*tensors: torch.Tensor) -> None:
@@ -42,6 +56,10 @@ def _chk(*tensors: torch.Tensor) -> None:
             raise RuntimeError("gptst_b200 ops need contiguous tensors")
 
 
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -52,6 +70,7 @@ def _p(t):
 def gproj_fwd(X, W, bias, res, *, node_grouped: bool, act: bool, prec: int):
     """X (B,T,N,D).  time-grouped: W (B*T,D,D)/(B,T,D,D); node-grouped: W (N,D,D)."""
     B, T, N, D = X.shape
+    X, W, bias, res = _c(X), _c(W), _c(bias), _c(res)
     _chk(X, W)
     Y = torch.empty_like(X)
     if node_grouped:
@@ -65,6 +84,7 @@ def gproj_fwd(X, W, bias, res, *, node_grouped: bool, act: bool, prec: int):
 
 def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dres: bool):
     B, T, N, D = X.shape
+    dY, Y, X, W = _c(dY), _c(Y), _c(X), _c(W)
     _chk(dY, X, W)
     if node_grouped:
         G, R, gs, rs = N, B * T, D, N * D
@@ -86,6 +106,7 @@ def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dre
 
 def tmix(x, M, out=None, *, transpose=False, accumulate=False):
     B, T, N, D = x.shape
+    x, M = _c(x), _c(M)
     _chk(x, M)
     if out is None:
         out = torch.empty_like(x)
@@ -96,6 +117,7 @@ def tmix(x, M, out=None, *, transpose=False, accumulate=False):
 
 def tmix_dM(dy, x):
     B, T, N, D = x.shape
+    dy, x = _c(dy), _c(x)
     _chk(dy, x)
     L = _lib.lib()
     splits = L.gptst_tmix_dM_splits(B, N)
@@ -146,6 +168,7 @@ class _CapCore(torch.autograd.Function):
         H, HT = dadj.shape[2], dyn.shape[1]
         L = _lib.lib()
         st = _stream()
+        _count(2)  # route_fwd + hop_fwd + recon share `st`
         c = torch.empty((B, T, H, N), device=x.device, dtype=torch.float32)
         s = torch.empty((B, T, H, D), device=x.device, dtype=torch.float32)
         _lib.check(L.gptst_cap_route_fwd(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), B, T, N, D, H, int(num_route),
@@ -167,6 +190,7 @@ class _CapCore(torch.autograd.Function):
         H, HT = c.shape[2], dyn.shape[1]
         L = _lib.lib()
         st = _stream()
+        _count(2)  # dv_dcr + hop_bwd + route_bwd share `st`
         dout = dout.contiguous()
         drecon, dWn, dbn, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True)
         dv = torch.empty_like(s)
