@@ -6,7 +6,7 @@
  *   - is stream-ordered and asynchronous: no allocation, no host synchronisation, no global state, so the
  *     calls can be captured into a CUDA graph;
  *   - returns 0 on success, a positive cudaError_t on a CUDA failure, -1 for a NULL/empty argument and
- *     -2 for an unsupported shape (D must be 64 or 128, T == 12, H <= 16, prec in {1,3}).
+ *     -2 for an unsupported shape (D must be 64 or 128, T == 12, H <= 15, prec in {1,3}).
  *
  * The reference (HKUDS/GPT-ST) has no FFI: the path is pure PyTorch.  Each function below replaces the
  * cited lines of /root/reference/model/Pretrain_model/GPTST.py; INTEGRATION.md shows the ctypes binding.
