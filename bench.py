@@ -288,24 +288,15 @@ def run_ours(args):
     model = GPTST_Model(cfg).to(dev)
     run_init(model, 0)
     dp.broadcast_parameters(model)
-    reducer = dp.FlatGradAllReduce(model.parameters()).attach()
-    opt = torch.optim.Adam(model.parameters(), lr=3e-3, eps=1e-8)
+    from gptst_b200.train import PretrainStep
+    reducer = dp.FlatGradAllReduce(model.parameters()) if world > 1 else None
+    stepper = PretrainStep(model, lr=3e-3, max_grad_norm=5.0, loss="probe", use_graph=not args.eager, reducer=reducer)
 
     # synthetic inputs (standard normal); distinct per rank
     gcpu = torch.Generator().manual_seed(100 + rank)
     nbuf = 4
     host = [torch.randn(B, T_STEPS, N, 3, generator=gcpu).pin_memory() for _ in range(nbuf)]
     resident = [h.to(dev) for h in host]
-    staging = torch.empty_like(resident[0])
-
-    def train_step(x):
-        opt.zero_grad(set_to_none=True)
-        outs = model(x, x, 1, epoch)
-        loss = probe_loss(outs, x, epoch, cfg.change_epoch)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
-        opt.step()
-        return loss
 
     def barrier():
         if world > 1:
@@ -314,16 +305,16 @@ def run_ours(args):
 
     def timed(nsteps, e2e):
         barrier()
-        l0 = ops.launch_count()
+        l0, r0 = ops.launch_count(), stepper.replays
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for i in range(nsteps):
             if e2e:
-                staging.copy_(host[i % nbuf], non_blocking=True)       # H2D of this step's batch from pinned memory
-                last = float(train_step(staging))                      # D2H read of the loss
+                # public API with HOST buffers: H2D of this step's batch from pinned memory, D2H read of the loss
+                last = float(stepper(host[i % nbuf], epoch))
             else:
-                last = train_step(resident[i % nbuf])
+                last = stepper(resident[i % nbuf], epoch)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -332,14 +323,14 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ops.launch_count() - l0, float(last)
+        launches = (ops.launch_count() - l0) + (stepper.replays - r0) * stepper.launches_per_step
+        return ms, launches, float(last)
 
-    random_seed = 1234 + rank
     import random
-    random.seed(random_seed)
-    torch.manual_seed(random_seed)
-    for i in range(max(3, args.warmup)):
-        train_step(resident[i % nbuf])
+    random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+    for i in range(max(4, args.warmup)):          # >= 3 eager warm-up steps + graph capture + first replay
+        stepper(resident[i % nbuf], epoch)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -348,6 +339,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else {}
     value = world * B * args.steps / (ms * 1e-3)
     value_e2e = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d_bytes = resident[0].numel() * 4 * world
 
     line = None
     if rank == 0:
@@ -358,15 +350,15 @@ def run_ours(args):
         step_bytes = (60 * 4 * B * T_STEPS * N * D) + (8 * 4 * B * T_STEPS * N * 10)
         line = {
             "metric": "pretrain samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core contractions, fp32 accumulate)"
             if ops.default_precision() == 3 else "tf32 operands, fp32 accumulate",
             "data": "synthetic", "config": workload_config(args.workload, B, world, epoch) | {
                 "l2": "no flush between steps: one step touches ~2 GB of activations/gradients >> 126 MB L2; "
                       "kernel roofline timed on rotating buffer sets > L2"},
-            "e2e": {"value": value_e2e, "unit": "samples/s", "h2d_bytes_per_step": staging.numel() * 4 * world,
+            "e2e": {"value": value_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "step_mode": "eager" if args.eager else "one CUDA graph per step (gptst_b200.train.PretrainStep)",
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + cap_hop_fwd + cap_recon + gproj_fwd), "
                          "the hypergraph + node-adaptive GCN block", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -400,6 +392,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--epoch", type=int, default=200, help="epoch argument passed to the model (mask phase)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager step (what an unmodified Run.py loop launches) instead of the graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

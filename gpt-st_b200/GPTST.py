@@ -184,6 +184,8 @@ class Hypergraph_encoder(nn.Module):
         self.neb4mask = nn.Parameter(torch.randn(self.num_node, self.embed_dim))
         # hook for parity tests: replaces the arg-max class labels (near-ties can flip between implementations)
         self.label_c_override = None
+        # graph replay hook: int64 device vector [order, adaptive_num, random_num] (see mask_plan)
+        self.plan_override = None
 
     # -- mask scorer (both phases), ref :326-332 / :338-343
     def _scores(self, source):
@@ -199,37 +201,57 @@ class Hypergraph_encoder(nn.Module):
         ada = int(total * tp)
         return ada, total - ada
 
+    def mask_plan(self, n_cells, epoch):
+        """Host half of the phase-2 mask: shuffled class order (ref :357-358) and the two budgets (ref :348-353) as one
+        int64 vector [order[0..H), adaptive_num, random_num].  Consumes python `random` exactly like the reference."""
+        ada_num, rnd_num = self._budgets(n_cells, epoch)
+        order = list(range(self.HS))
+        random.shuffle(order)
+        return torch.tensor(order + [ada_num, rnd_num], dtype=torch.int64)
+
     def _adaptive_mask(self, source, prob, epoch):
-        """Phase-2 mask (ref :344-413): whole classes in a shuffled order, then exact-count random fill."""
-        i0 = self.input_base_dim
+        """Phase-2 mask (ref :344-413): whole classes in a shuffled order until the adaptive budget is reached, the
+        last class sub-sampled, then an exact-count random fill.  Restated without host synchronisation: the class
+        selection loop of the reference (one `torch.sum(...)` D2H per class) becomes a 10-element prefix sum on the
+        device, and `order[:k]` with a device-side k becomes a scatter of (rank >= k).  Same draws, same sorts."""
+        i0, H = self.input_base_dim, self.HS
         if self.label_c_override is not None:
             label_c = self.label_c_override
         else:
             label_c = torch.sort(prob, dim=-1, descending=True)[1][..., 0]
         flat = label_c.reshape(-1)
-        ada_num, rnd_num = self._budgets(flat.numel(), epoch)
-        order = list(range(self.HS))
-        random.shuffle(order)
-        counts = torch.bincount(flat, minlength=self.HS).tolist()      # the only host sync of the mask logic
-        picked = total = 0
-        while total < ada_num:
-            total += counts[order[picked]]
-            picked += 1
-        lut = torch.zeros(self.HS, dtype=torch.int64)
-        if self.ada_type == "all" and picked >= 2:
-            lut[order[:picked - 1]] = 2                                # masked outright
-            lut[order[picked - 1]] = 1                                 # sub-sampled
-            n_full = sum(counts[k] for k in order[:picked - 1])
+        n = flat.numel()
+        dev = flat.device
+        if self.plan_override is not None:           # graph replay: a static device buffer refreshed by the caller
+            plan = self.plan_override
         else:
-            lut[order[:picked]] = 1
-            n_full = 0
-        role = lut.to(flat.device)[flat]
-        full = (role == 2).to(torch.int64)
-        part = (role == 1).to(torch.int64)
+            plan = self.mask_plan(n, epoch).to(dev)
+        order, ada, rnd = plan[:H], plan[H], plan[H + 1]
+        counts = torch.zeros(H, dtype=torch.int64, device=dev).scatter_add_(0, flat, torch.ones_like(flat))
+        co = counts[order]
+        picked = (torch.cumsum(co, 0) - co) < ada           # classes the reference's while-loop would add
+        npick = picked.sum()
+        idx = torch.arange(H, device=dev)
+        if self.ada_type == "all":
+            last = picked & (idx == npick - 1)
+            multi = npick >= 2
+            full_o = picked & ~last & multi                  # masked outright
+            part_o = torch.where(multi, last, picked)        # sub-sampled
+        else:
+            full_o = torch.zeros_like(picked)
+            part_o = picked
+        lut = torch.zeros(H, dtype=torch.int64, device=dev).scatter_(0, order, part_o.long() + 2 * full_o.long())
+        n_full = (co * full_o).sum()
+        role = lut[flat]
+        full = (role == 2).long()
+        part = (role == 1).long()
+        pos = torch.arange(n, device=dev)
         u1 = torch.rand_like(source[..., 0:1].reshape(-1))
-        m_ada = _exact_count_mask(part * u1, ada_num - n_full) * (1 - full)
+        o1 = torch.sort(part * u1, dim=0, descending=True)[1]
+        m_ada = torch.empty_like(o1).scatter_(0, o1, (pos >= (ada - n_full)).long()) * (1 - full)
         u2 = torch.rand_like(source[..., 0:1].reshape(-1))
-        m_rnd = _exact_count_mask(m_ada * u2, rnd_num)
+        o2 = torch.sort(m_ada * u2, dim=0, descending=True)[1]
+        m_rnd = torch.empty_like(o2).scatter_(0, o2, (pos >= rnd).long())
         final = (m_ada * m_rnd).reshape(label_c.shape).unsqueeze(-1)
         if i0 != 1:
             final = final.repeat(1, 1, 1, i0)

@@ -38,3 +38,22 @@ def probe_loss(outs, source, epoch: int, change_epoch: int = 10):
     if epoch > change_epoch:
         loss = loss + 0.1 * kl_sum(prob, hs)
     return loss
+
+
+def masked_mae_syncfree(pred, true, mask, mean: float, std: float, mask_value=0.0):
+    """Same value as masked_mae without the data-dependent `masked_select` (no host sync, CUDA-graph safe):
+    mean over {true*mask > thresh} of |true - pred| == sum(|.| * sel) / sum(sel)."""
+    p = (pred * std + mean) * mask
+    t = (true * std + mean) * mask
+    if mask_value is None:
+        return (t - p).abs().mean()
+    sel = (t > mask_value).to(p.dtype)
+    return ((t - p).abs() * sel).sum() / sel.sum()
+
+
+def pretrain_loss_syncfree(outs, source, epoch: int, change_epoch: int, mean: float, std: float, output_dim: int = 1):
+    flow_out, _, inv_mask, prob, hs1 = outs
+    loss = masked_mae_syncfree(flow_out, source[..., :output_dim], inv_mask, mean, std, 0.0)
+    if epoch > change_epoch:
+        loss = loss + 0.1 * kl_sum(prob, hs1)
+    return loss
