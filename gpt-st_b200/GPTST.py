@@ -20,6 +20,7 @@ GPU (LOCAL_RANK) works for data parallel training.
 """
 from __future__ import annotations
 
+import os
 import random
 
 import torch
@@ -73,13 +74,18 @@ class cap(nn.Module):
         # kept for state_dict compatibility; the kernels use tau_t = (t+1)/12 directly (ref :97,125)
         self.register_buffer("mask_template", torch.linspace(1, timesteps, steps=timesteps) / 12.0)
 
-    def forward(self, x, node_embeddings, time_eb, teb):
+    def tables(self, node_embeddings, time_eb, teb):
+        """Parameter-side contractions (independent of x): incidence logits, inter-cluster adjacency, node-adaptive weights."""
         if self.timesteps != 12:
             raise RuntimeError("cap: the reference (and the kernels) hard-wire 12 time steps")
         dadj = torch.einsum("btd,dhn->bthn", teb, self.adj)
         dyn = torch.einsum("bd,dhk->bhk", time_eb, self.t_adj)
         Wn = torch.einsum("nd,dio->nio", node_embeddings, self.weights_spa)
         bn = node_embeddings @ self.bias_spa
+        return dadj, dyn, Wn, bn
+
+    def forward(self, x, node_embeddings, time_eb, teb, tables=None):
+        dadj, dyn, Wn, bn = tables if tables is not None else self.tables(node_embeddings, time_eb, teb)
         out, c = ops.cap_core(x, self.ln_p.weight, self.ln_p.bias, dadj, dyn, Wn, bn, self.num_route)
         return out, c.unsqueeze(-1), dyn.detach()
 
@@ -94,11 +100,16 @@ class hyperTem(nn.Module):
         self.weights_pool = _uninit(embed_dim, dim_in, dim_out)
         self.bias_pool = _uninit(embed_dim, dim_out)
 
-    def forward(self, eb, node_embeddings, time_eb):
+    def tables(self, node_embeddings, time_eb):
+        """Parameter-side contractions (independent of eb): per-node T x T mix and time-adaptive weights."""
         A = torch.einsum("nk,kht->nht", node_embeddings, self.adj)
         Mn = torch.einsum("nht,nhs->nts", A, A)                      # two hops with no nonlinearity in between
         W = torch.einsum("btd,dio->btio", time_eb, self.weights_pool)
         bias = time_eb @ self.bias_pool
+        return Mn, W, bias
+
+    def forward(self, eb, node_embeddings, time_eb, tables=None):
+        Mn, W, bias = tables if tables is not None else self.tables(node_embeddings, time_eb)
         return ops.hypertem_core(eb, Mn, W, bias)
 
 
@@ -143,19 +154,28 @@ class STHCN(nn.Module):
         for i in (1, 2):
             setattr(self, f"cap{i}", cap(D, args.num_nodes, args.horizon, d, ds, args.HS, args.HT, args.num_route))
 
-    def forward(self, source, x_in):
+    def prologue(self, source):
+        """Everything of this STHCN that does not depend on the activations: the three time embeddings (ref :256-261)
+        and the adaptive tables of the six blocks.  GPTST_Model runs it on a side stream."""
         i0 = self.input_base_dim
         tf_in = source[:, :, 0, i0:i0 + 2]                             # day / week index of node 0 (ref :256-257)
         time_eb = self.time_feature1(tf_in)
         teb = self.time_feature1_(tf_in)
         time_eb_spg = self.time_feature2(tf_in)
         E, Es = self.node_embeddings, self.node_embeddings_spg
-        x = self.hyperTem1(x_in, E, time_eb)
-        x, HS1, _ = self.cap1(x, Es, time_eb_spg, teb)
-        x = self.hyperTem2(x, E, time_eb)
-        x = self.hyperTem3(x, E, time_eb)
-        x, HS3, _ = self.cap2(x, Es, time_eb_spg, teb)
-        x = self.hyperTem4(x, E, time_eb)
+        return {"ht": [getattr(self, f"hyperTem{i}").tables(E, time_eb) for i in range(1, 5)],
+                "cap": [getattr(self, f"cap{i}").tables(Es, time_eb_spg, teb) for i in (1, 2)]}
+
+    def forward(self, source, x_in, pro=None):
+        if pro is None:
+            pro = self.prologue(source)
+        ht, cp = pro["ht"], pro["cap"]
+        x = self.hyperTem1(x_in, None, None, ht[0])
+        x, HS1, _ = self.cap1(x, None, None, None, cp[0])
+        x = self.hyperTem2(x, None, None, ht[1])
+        x = self.hyperTem3(x, None, None, ht[2])
+        x, HS3, _ = self.cap2(x, None, None, None, cp[1])
+        x = self.hyperTem4(x, None, None, ht[3])
         return x, HS1, HS3
 
 
@@ -218,7 +238,7 @@ class Hypergraph_encoder(nn.Module):
         if self.label_c_override is not None:
             label_c = self.label_c_override
         else:
-            label_c = torch.sort(prob, dim=-1, descending=True)[1][..., 0]
+            label_c = torch.argmax(prob, dim=-1)      # == sort(descending)[..., 0] of the reference (:344-345) up to exact ties
         flat = label_c.reshape(-1)
         n = flat.numel()
         dev = flat.device
@@ -257,11 +277,11 @@ class Hypergraph_encoder(nn.Module):
             final = final.repeat(1, 1, 1, i0)
         return final
 
-    def forward(self, source, label, epoch=None):
+    def forward(self, source, label, epoch=None, pro=None):
         i0 = self.input_base_dim
         flow = source[..., 0:i0]
         if self.mode != "pretrain":
-            enc, _, _ = self.STHCN_encode(source, self.dim_in_flow(flow))
+            enc, _, _ = self.STHCN_encode(source, self.dim_in_flow(flow), pro)
             return enc
         if epoch <= self.change_epoch:
             u = torch.rand_like(flow.reshape(-1))
@@ -273,7 +293,10 @@ class Hypergraph_encoder(nn.Module):
             final_mask = self._adaptive_mask(source, prob, epoch)
         final_mask = final_mask.detach()
         masked = torch.where(final_mask == 0, torch.full_like(flow, float(self.scaler_zeros)), final_mask * flow)
-        enc, HS1, _ = self.STHCN_encode(source, self.dim_in_flow(masked))
+        x_in = self.dim_in_flow(masked)
+        if pro is not None and "event" in pro:
+            torch.cuda.current_stream().wait_event(pro["event"])
+        enc, HS1, _ = self.STHCN_encode(source, x_in, pro)
         return enc, final_mask[..., :i0], prob, HS1.squeeze(-1).transpose(-1, -2)
 
 
@@ -286,8 +309,10 @@ class Hypergraph_decoder(nn.Module):
         self.STHCN_decode = STHCN(args)
         self.dim_flow_out = nn.Linear(self.hidden_dim, self.input_base_dim, bias=True)
 
-    def forward(self, source, flow_encode_eb):
-        flow_decode, _, _ = self.STHCN_decode(source, flow_encode_eb)
+    def forward(self, source, flow_encode_eb, pro=None):
+        if pro is not None and "event" in pro:
+            torch.cuda.current_stream().wait_event(pro["event"])
+        flow_decode, _, _ = self.STHCN_decode(source, flow_encode_eb, pro)
         return self.dim_flow_out(flow_decode), flow_decode
 
 
@@ -303,10 +328,52 @@ class GPTST_Model(nn.Module):
             raise ValueError("gptst_b200 kernels are built for hidden_dim 64 or 128")
         self.encoder = Hypergraph_encoder(args)
         self.decoder = Hypergraph_decoder(args)
+        # overlap the parameter-side prologues on side streams (pretrain mode); plain attributes, deepcopy-safe
+        self.side_streams = os.environ.get("GPTST_B200_SIDE_STREAMS", "1") != "0"
+        self._streams = None
+
+    def __deepcopy__(self, memo):
+        streams, self._streams = self._streams, None          # CUDA stream handles are not copyable state
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            import copy as _copy
+            for k, v in self.__dict__.items():
+                setattr(new, k, _copy.deepcopy(v, memo))
+            return new
+        finally:
+            self._streams = streams
+
+    def _side_prologues(self, source):
+        """Run the activation-independent halves of both STHCNs on two side streams, concurrently with the mask
+        scoring on the caller's stream.  Under CUDA-graph capture the fork/join becomes parallel graph branches; the
+        autograd engine replays the same streams in backward, so the table gradients overlap the big kernels too."""
+        main = torch.cuda.current_stream()
+        dev = source.device
+        key = (dev.index, main.cuda_stream)
+        if self._streams is None or self._streams[0] != key:
+            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        fork = torch.cuda.Event()
+        fork.record(main)
+        out = []
+        for stream, sthcn in ((self._streams[1], self.encoder.STHCN_encode), (self._streams[2], self.decoder.STHCN_decode)):
+            stream.wait_event(fork)
+            with torch.cuda.stream(stream):
+                pro = sthcn.prologue(source)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            for grp in pro["ht"] + pro["cap"]:
+                for t in grp:
+                    t.record_stream(main)
+            pro["event"] = ev
+            out.append(pro)
+        return out
 
     def forward_pretrain(self, source, label, batch_seen=None, epoch=None):
-        flow_encode_eb, mask, probability, HS1 = self.encoder(source, label, epoch)
-        flow_out, flow_decode = self.decoder(source, flow_encode_eb)
+        enc_pro, dec_pro = self._side_prologues(source) if self.side_streams else (None, None)
+        flow_encode_eb, mask, probability, HS1 = self.encoder(source, label, epoch, enc_pro)
+        flow_out, flow_decode = self.decoder(source, flow_encode_eb, dec_pro)
         return flow_out, flow_decode, 1 - mask, probability, HS1
 
     def forward_fune(self, source, label):

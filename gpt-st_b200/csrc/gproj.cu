@@ -12,6 +12,8 @@
 //
 // Backward (same addressing):   dy = dY * act'(Y)
 //   dX[g][r][:]  = dy . W[g]^T        dW[g] = sum_r X^T dy        dbias[g] = sum_r dy        dRes = dy
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gptst {
@@ -265,6 +267,20 @@ static cudaError_t launch_bwd(const float* dY, const float* Y, const float* X, c
 
 }  // namespace gptst
 
+namespace gptst {
+// tcgen05 / TMEM implementation for D = 64 (gproj_umma.cu)
+cudaError_t gproj_fwd_umma(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R,
+                           long gs, long rs, int act, int prec, cudaStream_t st);
+static bool use_umma() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPTST_B200_GPROJ");
+        v = (e && e[0] == 'm') ? 0 : 1;   // GPTST_B200_GPROJ=mma selects the legacy mma.sync kernel (A/B testing)
+    }
+    return v == 1;
+}
+}  // namespace gptst
+
 using namespace gptst;
 
 #define DISPATCH_D_PREC(D_, P_, CALL)                                          \
@@ -291,6 +307,8 @@ extern "C" int gptst_gproj_fwd(const float* X, const float* W, const float* bias
                                int R, long group_stride, long row_stride, int D, int act, int prec, void* stream) {
     if (!X || !W || !Y || G <= 0 || R <= 0) return -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (D == 64 && (prec == 1 || prec == 3) && use_umma())
+        return (int)gproj_fwd_umma(X, W, bias, Res, Y, G, R, group_stride, row_stride, act, prec, st);
     int splits = gptst_gproj_splits(G, R, D);
 #define CALL(DD, PP) return (int)launch_fwd<DD, PP>(X, W, bias, Res, Y, G, R, group_stride, row_stride, act, splits, st)
     DISPATCH_D_PREC(D, prec, CALL);
