@@ -377,8 +377,15 @@ def run_ours(args):
                                     "sample": f"{done} full training steps at batch {B} (after 1 warm-up) on {cores} host threads"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # a CUDA graph that captured NCCL kernels must be released before the communicator goes away; destroying the
+        # process group with the graph alive dead-locks (observed), so: drop graphs, sync, barrier, hard-exit.
+        stepper._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
     return 0
 
 
