@@ -35,17 +35,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
+// TF32 operand preparation.  NOTE: on sm_100a `cvt.rna.tf32.f32` is emulated by a ~15-instruction sequence
+// (observed in SASS: FSETP/SEL/LOP3/VIADD 0x1000), which made every kernel issue-bound.  The tensor cores ignore
+// the low 13 mantissa bits of a tf32 operand, so:
+//   1xTF32 : feed the fp32 bits as they are (truncation -- what cuBLAS' TF32 mode does as well);
+//   3xTF32 : hi = x with the low 13 bits cleared (1 LOP3), lo = x - hi (exact in fp32, 1 FADD).  hi + lo == x exactly,
+//            and lo itself is consumed with ~11 significant bits, so the dropped part is < 2^-21 |x|.
 template <int PREC>
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = f2tf32(x);
-    if (PREC == PREC_3XTF32) lo = f2tf32(x - __uint_as_float(hi));
-    else lo = 0u;
+    const uint32_t b = __float_as_uint(x);
+    if (PREC == PREC_3XTF32) {
+        hi = b & 0xffffe000u;
+        lo = __float_as_uint(x - __uint_as_float(hi));
+    } else {
+        hi = b;
+        lo = 0u;
+    }
 }
 
 // D(16x8) += A(16x8, row) * B(8x8, col), tf32 operands, fp32 accumulate.

@@ -271,11 +271,23 @@ namespace gptst {
 // tcgen05 / TMEM implementation for D = 64 (gproj_umma.cu)
 cudaError_t gproj_fwd_umma(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R,
                            long gs, long rs, int act, int prec, cudaStream_t st);
+cudaError_t gproj_bwd_umma(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,
+                           float* dRes, int G, int R, long gs, long rs, int act, int prec, int splits, cudaStream_t st);
 static bool use_umma() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GPTST_B200_GPROJ");
         v = (e && e[0] == 'm') ? 0 : 1;   // GPTST_B200_GPROJ=mma selects the legacy mma.sync kernel (A/B testing)
+    }
+    return v == 1;
+}
+// The tcgen05(dX)+mma.sync(dW) backward is correct but (one CTA per SM, serial phases) still a little slower than the
+// two-CTA mma.sync kernel on PEMS08 shapes; opt-in with GPTST_B200_GPROJ_BWD=umma until it is pipelined.
+static bool use_umma_bwd() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPTST_B200_GPROJ_BWD");
+        v = (e && e[0] == 'u') ? 1 : 0;
     }
     return v == 1;
 }
@@ -322,6 +334,8 @@ extern "C" int gptst_gproj_bwd(const float* dY, const float* Y, const float* X, 
     if (!dY || !X || !W || !dX || !dW_part || !dbias_part || G <= 0 || R <= 0 || splits <= 0) return -1;
     if (act && !Y) return -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (D == 64 && (prec == 1 || prec == 3) && use_umma_bwd())
+        return (int)gproj_bwd_umma(dY, Y, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride, act, prec, splits, st);
 #define CALL(DD, PP) \
     return (int)launch_bwd<DD, PP>(dY, Y, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride, act, splits, st)
     DISPATCH_D_PREC(D, prec, CALL);
