@@ -283,13 +283,21 @@ class Hypergraph_encoder(nn.Module):
         if self.mode != "pretrain":
             enc, _, _ = self.STHCN_encode(source, self.dim_in_flow(flow), pro)
             return enc
+        score = pro.get("score") if pro is not None else None     # (prob, event) computed on a side stream
         if epoch <= self.change_epoch:
             u = torch.rand_like(flow.reshape(-1))
             final_mask = _exact_count_mask(u, int(u.shape[0] * self.mask_ratio))
             final_mask = final_mask.reshape(-1, self.horizon, self.num_node, i0)
-            prob = self._scores(source)
+            if score is None:
+                prob = self._scores(source)
+            else:
+                prob = score[0]                                   # joined by the caller before the loss
         else:
-            prob = self._scores(source)
+            if score is None:
+                prob = self._scores(source)
+            else:
+                torch.cuda.current_stream().wait_event(score[1])
+                prob = score[0]
             final_mask = self._adaptive_mask(source, prob, epoch)
         final_mask = final_mask.detach()
         masked = torch.where(final_mask == 0, torch.full_like(flow, float(self.scaler_zeros)), final_mask * flow)
@@ -353,10 +361,19 @@ class GPTST_Model(nn.Module):
         dev = source.device
         key = (dev.index, main.cuda_stream)
         if self._streams is None or self._streams[0] != key:
-            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            self._streams = (key, torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         fork = torch.cuda.Event()
         fork.record(main)
         out = []
+        # mask scorer (teb4mask + MLP_RL + softmax) on its own stream: off the critical path in the random-mask phase, and
+        # its backward (KL branch) overlaps the main backward chain in the adaptive phase
+        s3 = self._streams[3]
+        s3.wait_event(fork)
+        with torch.cuda.stream(s3):
+            prob = self.encoder._scores(source)
+            ev3 = torch.cuda.Event()
+            ev3.record(s3)
+        prob.record_stream(main)
         for stream, sthcn in ((self._streams[1], self.encoder.STHCN_encode), (self._streams[2], self.decoder.STHCN_decode)):
             stream.wait_event(fork)
             with torch.cuda.stream(stream):
@@ -368,12 +385,15 @@ class GPTST_Model(nn.Module):
                     t.record_stream(main)
             pro["event"] = ev
             out.append(pro)
+        out[0]["score"] = (prob, ev3)
         return out
 
     def forward_pretrain(self, source, label, batch_seen=None, epoch=None):
         enc_pro, dec_pro = self._side_prologues(source) if self.side_streams else (None, None)
         flow_encode_eb, mask, probability, HS1 = self.encoder(source, label, epoch, enc_pro)
         flow_out, flow_decode = self.decoder(source, flow_encode_eb, dec_pro)
+        if enc_pro is not None:
+            torch.cuda.current_stream().wait_event(enc_pro["score"][1])   # join the scorer stream before the outputs are used
         return flow_out, flow_decode, 1 - mask, probability, HS1
 
     def forward_fune(self, source, label):

@@ -108,43 +108,46 @@ __global__ void __launch_bounds__(256) gproj_fwd_kernel(const float* __restrict_
 }
 
 // dW / dbias partial layout: [gridDim.y][G][D*D] and [gridDim.y][G][D]; the host sums over the leading dim.
+// 64-row tiles and a single fp32 copy of W[g] (operands are split on the fly: 2 instructions) keep the CTA at ~54 KB
+// of shared memory for D = 64, i.e. four CTAs (32 warps) per SM to hide the global-load latency of the tile loop.
+template <int D>
+struct GProjBwdCfg {
+    static constexpr int BM = 64;
+    static constexpr int WM = BM / 16;                  // 4 warps along rows
+    static constexpr int WN = 8 / WM;                   // 2 warps along columns
+    static constexpr int NT = D / 8 / WN;               // n-tiles per warp (dX)
+    static constexpr int LDW = D + 4;                   // B(k=o,n=i) = W[i][o]  (n-major)
+    static constexpr int LDX = D + 8;                   // X read transposed for dW
+    static constexpr int LDY = D + 4;                   // dy as A row-major (and k-major B for dW)
+};
+
 template <int D, int PREC>
 __global__ void __launch_bounds__(256) gproj_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y,
                                                         const float* __restrict__ X, const float* __restrict__ W,
                                                         float* __restrict__ dX, float* __restrict__ dWp,
                                                         float* __restrict__ dbp, float* __restrict__ dRes, int G, int R,
                                                         long group_stride, long row_stride, int act) {
-    using C = GProjCfg<D>;
+    using C = GProjBwdCfg<D>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* Wh = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* Wl = Wh + D * C::LDW_B;
-    float* Xs = reinterpret_cast<float*>(Wl + (PREC == PREC_3XTF32 ? D * C::LDW_B : 0));
-    float* Ys = Xs + C::BM * C::LDX_B;
-    float* red = Ys + C::BM * C::LDY_B;  // [256/D][D] column partial sums
+    float* Ws = reinterpret_cast<float*>(smem_raw);     // [D][LDW]  W[i][o]
+    float* Xs = Ws + D * C::LDW;                        // [BM][LDX]
+    float* Ys = Xs + C::BM * C::LDX;                    // [BM][LDY] dy
+    float* red = Ys + C::BM * C::LDY;                   // [256/D][D] column partial sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % C::WM, wn = warp / C::WM;
     const int g = blockIdx.x;
     const float* Wg = W + (size_t)g * D * D;
-    // W_s[i][o] = W[i][o]; dX = dy . W^T  ->  B(k=o, n=i) = W_s[n][k]  (n-major)
     for (int i = tid; i < D * D / 4; i += 256) {
         int k = (i * 4) / D, n = (i * 4) % D;
-        float4 w = *reinterpret_cast<const float4*>(Wg + (size_t)i * 4);
-        float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t hi, lo;
-            split_tf32<PREC>(wv[j], hi, lo);
-            Wh[k * C::LDW_B + n + j] = hi;
-            if (PREC == PREC_3XTF32) Wl[k * C::LDW_B + n + j] = lo;
-        }
+        *reinterpret_cast<float4*>(Ws + k * C::LDW + n) = *reinterpret_cast<const float4*>(Wg + (size_t)i * 4);
     }
-    // dW accumulators: output D x D, tiles of 16 x 8; warp owns m-tile set and n-tile set
-    constexpr int MT = D / 16, NTT = D / 8;            // m-tiles, n-tiles of dW
-    constexpr int WMG = (MT >= 8) ? 8 : MT;            // warps along m
-    constexpr int WNG = 8 / WMG;                       // warps along n
-    constexpr int MT_W = MT / WMG;                     // m-tiles per warp (1)
-    constexpr int NT_W = NTT / WNG;                    // n-tiles per warp
+    // dW accumulators: output D x D, tiles of 16 x 8; warp owns one m-tile and NT_W n-tiles
+    constexpr int MT = D / 16, NTT = D / 8;
+    constexpr int WMG = (MT >= 8) ? 8 : MT;
+    constexpr int WNG = 8 / WMG;
+    constexpr int MT_W = MT / WMG;
+    constexpr int NT_W = NTT / WNG;
     static_assert(MT_W == 1, "dW tiling");
     const int gm = warp % WMG, gn = warp / WMG;
     float gacc[NT_W][4];
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(256) gproj_bwd_kernel(const float* __restrict_
                 }
                 if (dRg) *reinterpret_cast<float4*>(dRg + off) = d;
             }
-            *reinterpret_cast<float4*>(Xs + r * C::LDX_B + c) = x;
-            *reinterpret_cast<float4*>(Ys + r * C::LDY_B + c) = d;
+            *reinterpret_cast<float4*>(Xs + r * C::LDX + c) = x;
+            *reinterpret_cast<float4*>(Ys + r * C::LDY + c) = d;
         }
         __syncthreads();
         // ---- dbias: column sums of dy
@@ -187,17 +190,16 @@ __global__ void __launch_bounds__(256) gproj_bwd_kernel(const float* __restrict_
             const int c = tid % D, part = tid / D;
             float s = 0.f;
             if (part < PARTS)
-                for (int r = part; r < C::BM; r += PARTS) s += Ys[r * C::LDY_B + c];
+                for (int r = part; r < C::BM; r += PARTS) s += Ys[r * C::LDY + c];
             if (part < PARTS) red[part * D + c] = s;
         }
-        // ---- dX = dy . W^T
+        // ---- dX = dy . W^T       B(k=o, n=i) = Ws[n][k]
         {
             float acc[C::NT][4];
 #pragma unroll
             for (int nt = 0; nt < C::NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
             const int ncol0 = wn * C::NT * 8;
-            warp_gemm_presplit<D, C::NT, PREC, false>(acc, Ys + wm * 16 * C::LDY_B, C::LDY_B, Wh + ncol0 * C::LDW_B,
-                                                      Wl + ncol0 * C::LDW_B, C::LDW_B, lane);
+            warp_gemm<D, C::NT, PREC, false, false>(acc, Ys + wm * 16 * C::LDY, C::LDY, Ws + ncol0 * C::LDW, C::LDW, lane);
             const int gq = lane >> 2, tq = lane & 3;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256) gproj_bwd_kernel(const float* __restrict_
             }
         }
         // ---- dW += X^T . dy      (M = i, N = o, K = rows of this tile; zero rows contribute nothing)
-        warp_gemm<C::BM, NT_W, PREC, true, true>(gacc, Xs + gm * 16, C::LDX_B, Ys + gn * NT_W * 8, C::LDY_B, lane);
+        warp_gemm<C::BM, NT_W, PREC, true, true>(gacc, Xs + gm * 16, C::LDX, Ys + gn * NT_W * 8, C::LDY, lane);
         __syncthreads();
         if (tid < D) {
             constexpr int PARTS = 256 / D;
@@ -240,9 +242,9 @@ static size_t gproj_fwd_smem(int prec) {
     return (size_t)(prec == PREC_3XTF32 ? 2 : 1) * D * C::LDW_F * 4 + (size_t)C::BM * C::LDX_F * 4 + D * 4;
 }
 template <int D>
-static size_t gproj_bwd_smem(int prec) {
-    using C = GProjCfg<D>;
-    return (size_t)(prec == PREC_3XTF32 ? 2 : 1) * D * C::LDW_B * 4 + (size_t)C::BM * (C::LDX_B + C::LDY_B) * 4 + 256 * 4;
+static size_t gproj_bwd_smem(int) {
+    using C = GProjBwdCfg<D>;
+    return (size_t)D * C::LDW * 4 + (size_t)C::BM * (C::LDX + C::LDY) * 4 + 256 * 4;
 }
 
 template <int D, int PREC>
