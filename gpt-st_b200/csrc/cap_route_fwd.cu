@@ -14,6 +14,8 @@
 // with the same permutation), so the softmax output never leaves registers.
 // The N-reduction is finished with a deterministic cross-warp tree in shared memory and, when the slab is
 // split over a cluster, a DSMEM all-gather of the per-CTA partial (H+1) x D sums.
+#include <cstdlib>
+
 #include "cap_common.cuh"
 
 namespace gptst {
@@ -277,10 +279,21 @@ __global__ void __launch_bounds__(256, 2) cap_route_fwd_kernel(const float* __re
     if (CS > 1) cluster.sync();  // peers may still be reading this CTA's `part` through DSMEM
 }
 
+static int min_cluster() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPTST_B200_ROUTE_CLUSTER");   // tuning knob: smallest cluster size to consider
+        v = e ? atoi(e) : 1;   // measured on B200 (N=170, D=64): cluster 1 -> 177 us, 2 -> 226 us, 4 -> 294 us for cap forward
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
 static int pick_cluster(int N, int D, int H, int* rpc_out) {
     static const int sizes[5] = {1, 2, 4, 8, 16};
     for (int i = 0; i < 5; ++i) {
         int cs = sizes[i];
+        if (cs < min_cluster() && N > 32 * cs) continue;   // more, smaller CTAs per slab: more warps in flight per SM
         int rpc = (N + cs - 1) / cs;
         rpc = (rpc + 15) / 16 * 16;
         if (rf_smem_floats(D, H, rpc) * 4 <= kSmemMax) {
