@@ -259,6 +259,11 @@ def hypertem_forward_time(N, D, B, iters=20):
     return 8 * B * T_STEPS * N * D, statistics.median(times)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one cap forward, from the committed
+# `ncu --set full` capture (profiles/ncu_cap_forward_r01.md); only known for the geometry that was captured.
+NCU_TRAFFIC_BYTES = {("pems08", 64): 124.8e6}
+
+
 def measured_peak():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -362,7 +367,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + cap_hop_fwd + cap_recon + gproj_fwd), "
                          "the hypergraph + node-adaptive GCN block", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, B)), "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
             "roofline_hypertem_fwd": {"achieved": ht_algo / (ht_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ht_ms,
                                       "algorithmic_bytes": ht_algo, "frac": ht_algo / (ht_ms * 1e-3) / 1e9 / peak},
             "step_roofline": {"algorithmic_bytes": step_bytes, "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
