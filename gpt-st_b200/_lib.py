@@ -28,6 +28,9 @@ SIGNATURES = {
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route_bwd_parts": (_i, [_i, _i, _i, _i, _i]),
     "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_loss_parts": (_i, []),
+    "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
+                                C.c_float, _f]),
     "gptst_version": (C.c_char_p, []),
 }
 

@@ -76,19 +76,29 @@ __device__ void route_pass_mma(const RF& sm, int mode, bool use_v, int H, int RP
         const int nb = grp * 8;
         float z[4] = {0.f, 0.f, 0.f, 0.f};   // (h0,na) (h0,nb) (h1,na) (h1,nb)
         if (mode != 0 && use_v) {
+            // six independent accumulators (3 split terms x even/odd k-step) keep the dependent mma chain at D/16 instead
+            // of 3*D/8: with 2-4 warps per scheduler the chain latency, not the tensor pipe, was the limiter
+            float zz[6][4];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) zz[i][0] = zz[i][1] = zz[i][2] = zz[i][3] = 0.f;
 #pragma unroll
             for (int k0 = 0; k0 < D; k0 += 8) {
+                const int par = (k0 >> 3) & 1;
                 uint32_t ah[4], al[4], bh[2], bl2[2];
                 ah[0] = sm.vh[h0 * sm.ldv + k0 + tq];     ah[1] = sm.vh[h1 * sm.ldv + k0 + tq];
                 ah[2] = sm.vh[h0 * sm.ldv + k0 + tq + 4]; ah[3] = sm.vh[h1 * sm.ldv + k0 + tq + 4];
+                split_tf32<PREC>(sm.Ps[(size_t)(nb + g) * sm.ldp + k0 + tq], bh[0], bl2[0]);
+                split_tf32<PREC>(sm.Ps[(size_t)(nb + g) * sm.ldp + k0 + tq + 4], bh[1], bl2[1]);
                 if (PREC == PREC_3XTF32) {
                     al[0] = sm.vl[h0 * sm.ldv + k0 + tq];     al[1] = sm.vl[h1 * sm.ldv + k0 + tq];
                     al[2] = sm.vl[h0 * sm.ldv + k0 + tq + 4]; al[3] = sm.vl[h1 * sm.ldv + k0 + tq + 4];
-                } else { al[0] = al[1] = al[2] = al[3] = 0u; }
-                split_tf32<PREC>(sm.Ps[(size_t)(nb + g) * sm.ldp + k0 + tq], bh[0], bl2[0]);
-                split_tf32<PREC>(sm.Ps[(size_t)(nb + g) * sm.ldp + k0 + tq + 4], bh[1], bl2[1]);
-                mma_split<PREC>(z, ah, al, bh, bl2);
+                    mma_tf32(zz[par], al, bh);
+                    mma_tf32(zz[2 + par], ah, bl2);
+                }
+                mma_tf32(zz[4 + par], ah, bh);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z[i] = ((zz[0][i] + zz[1][i]) + (zz[2][i] + zz[3][i])) + (zz[4][i] + zz[5][i]);
         }
         const int na = nb + 2 * tq, nbb = na + 1;
         const bool va = na < nloc, vb = nbb < nloc;

@@ -242,3 +242,53 @@ def node_adaptive_proj(x, Wn, bn, prec=None):
 def time_adaptive_proj(x, Wt, bt, prec=None):
     """y[b,t,n,:] = LReLU(x[b,t,n,:] . Wt[b,t] + bt[b,t])  GPTST.py:29-32"""
     return _AdaptiveProj.apply(x, Wt, bt, False, default_precision() if prec is None else prec)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused pre-training loss (row f2): value + analytic gradients in one pass
+# ---------------------------------------------------------------------------------------------------
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, flow_out, prob, source, inv_mask, hs, mode, mean, std, thr, kl_w):
+        o = flow_out.contiguous()
+        _chk(o)
+        src = source if source.is_contiguous() else source.contiguous()
+        inv = inv_mask.contiguous()
+        if inv.dtype != torch.int64:
+            raise RuntimeError("inv_mask must be int64 (the model returns 1 - mask as int64)")
+        ibd = o.shape[-1]
+        cells = o.numel() // ibd
+        H = hs.shape[-1] if kl_w != 0.0 else 0
+        L = _lib.lib()
+        st = _stream()
+        _count(1)
+        d_o = torch.empty_like(o)
+        d_p = torch.empty_like(prob) if kl_w != 0.0 else None
+        part = torch.empty(3 * L.gptst_loss_parts(), device=o.device, dtype=torch.float32)
+        out = torch.empty(3, device=o.device, dtype=torch.float32)
+        pc = prob.contiguous() if kl_w != 0.0 else None
+        hc = hs.contiguous() if kl_w != 0.0 else None
+        _lib.check(L.gptst_pretrain_loss(_p(o), _p(src), _p(inv), _p(pc), _p(hc), _p(d_o), _p(d_p), _p(part), _p(out), cells, ibd,
+                                         src.shape[-1], H, int(mode), float(mean), float(std), float(thr), float(kl_w), st),
+                   "gptst_pretrain_loss")
+        ctx.save_for_backward(d_o, d_p if d_p is not None else d_o)
+        ctx.has_kl = kl_w != 0.0
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g, _g2):
+        d_o, d_p = ctx.saved_tensors
+        return d_o * g, (d_p * g) if ctx.has_kl else None, None, None, None, None, None, None, None, None
+
+
+def fused_probe_loss(outs, source, use_kl: bool, kl_weight: float = 0.1):
+    """mean|(o - x)*mask| (+ kl_weight * KL(sum)) -- one fused kernel pair; returns the scalar loss."""
+    flow_out, _, inv_mask, prob, hs = outs
+    return _FusedLoss.apply(flow_out, prob, source, inv_mask, hs, 0, 0.0, 1.0, 0.0, kl_weight if use_kl else 0.0)[0]
+
+
+def fused_mask_mae_loss(outs, source, use_kl: bool, mean: float, std: float, mask_value: float = 0.0, kl_weight: float = 0.1):
+    """Reference training loss (Run.py:91-101 + BasicTrainer.py:84-86) as one fused kernel pair."""
+    flow_out, _, inv_mask, prob, hs = outs
+    return _FusedLoss.apply(flow_out, prob, source, inv_mask, hs, 1, mean, std, mask_value, kl_weight if use_kl else 0.0)[0]

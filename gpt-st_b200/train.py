@@ -35,9 +35,15 @@ class PretrainStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, eps=1e-8, capturable=use_graph, foreach=True)
         if isinstance(loss, str):
+            from . import ops as _ops
             if loss == "probe":
-                self.loss_fn = lambda outs, src, ep: probe_loss(outs, src, ep, self.enc.change_epoch)
+                self.loss_fn = lambda outs, src, ep: _ops.fused_probe_loss(outs, src, ep > self.enc.change_epoch)
             elif loss == "mask_mae":
+                self.loss_fn = lambda outs, src, ep: _ops.fused_mask_mae_loss(outs, src, ep > self.enc.change_epoch,
+                                                                              scaler_mean, scaler_std)
+            elif loss == "probe_torch":
+                self.loss_fn = lambda outs, src, ep: probe_loss(outs, src, ep, self.enc.change_epoch)
+            elif loss == "mask_mae_torch":
                 self.loss_fn = lambda outs, src, ep: pretrain_loss_syncfree(outs, src, ep, self.enc.change_epoch, scaler_mean,
                                                                             scaler_std, model.output_dim)
             else:

@@ -73,6 +73,17 @@ int gptst_cap_route_bwd(const float* x, const float* Wp, const float* bp, const 
                         const float* dcr, float* dx_io, float* ddadj, float* dWp_part, float* dbp_part, int B, int T,
                         int N, int D, int H, int prec, void* stream);
 
+/* ---- fused pre-training loss + analytic gradients ------------------------------------
+ * mode 0: probe loss mean|(o - x)*m| ; mode 1: masked MAE of Run.py:91-101 / lib/metrics.py:11-18 (inverse z-score with
+ * mean/std, keep true*m > thr) ; plus kl_w * KLDivLoss(sum)(log prob, hs) (BasicTrainer.py:84-86) when kl_w != 0.
+ * o (cells, ibd) fp32, src (cells, src_stride) fp32 (first ibd channels are the flow), inv_mask (cells, ibd) int64,
+ * prob / hs (cells, H).  Outputs: d_o = dloss/do, d_prob = dloss/dprob, out = {loss, mae, kl_sum};
+ * part = scratch of 3*gptst_loss_parts() floats.  Two stream-ordered launches, deterministic.                  */
+int gptst_loss_parts(void);
+int gptst_pretrain_loss(const float* o, const float* src, const long long* inv_mask, const float* prob, const float* hs,
+                        float* d_o, float* d_prob, float* part, float* out, long n_cells, int ibd, int src_stride, int H,
+                        int mode, float mean, float std_, float thr, float kl_w, void* stream);
+
 /* library identification: "gptst_b200 <version> sm_100a" */
 const char* gptst_version(void);
 

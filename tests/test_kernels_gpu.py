@@ -224,3 +224,36 @@ def test_cpu_tensors_are_rejected():
     from gptst_b200 import ops
     with pytest.raises(RuntimeError):
         ops.tmix(torch.zeros(1, 12, 4, 64), torch.zeros(4, 12, 12))
+
+
+@pytest.mark.parametrize("use_kl", [False, True])
+@pytest.mark.parametrize("mode", ["probe", "mask_mae"])
+@pytest.mark.parametrize("ibd", [1, 2])
+def test_fused_loss_matches_reference_losses(mode, use_kl, ibd):
+    """Row f2: fused loss value and gradients vs the torch restatement of Run.py:91-101 / BasicTrainer.py:84-86."""
+    from gptst_b200 import ops
+    from gptst_b200.losses import masked_mae, kl_sum
+    B, N, H = 3, 37, 10
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(B, 12, N, ibd + 2, generator=g).cuda()
+    o = torch.randn(B, 12, N, ibd, generator=g).cuda().requires_grad_()
+    inv = (torch.rand(B, 12, N, ibd, generator=g) < 0.25).long().cuda()
+    prob = torch.softmax(torch.randn(B, 12, N, H, generator=g), -1).cuda().requires_grad_()
+    hs = torch.softmax(torch.randn(B, 12, N, H, generator=g) * 3, -1).cuda()
+    mean, std = 229.6, 145.6
+    if mode == "probe":
+        want = ((o - src[..., :ibd]) * inv).abs().mean()
+        got = ops.fused_probe_loss((o, None, inv, prob, hs), src, use_kl)
+    else:
+        want = masked_mae(o, src[..., :ibd], inv, mean, std, 0.0)
+        got = ops.fused_mask_mae_loss((o, None, inv, prob, hs), src, use_kl, mean, std)
+    if use_kl:
+        want = want + 0.1 * kl_sum(prob, hs)
+    assert abs(got.item() - want.item()) <= 2e-5 * max(1.0, abs(want.item()))
+    go, gp = torch.autograd.grad(want, [o, prob], allow_unused=True)
+    ho, hp = torch.autograd.grad(got, [o, prob], allow_unused=True)
+    check(ho, go.double(), 1e-5, "fused loss d/d flow_out")
+    if use_kl:
+        check(hp, gp.double(), 1e-5, "fused loss d/d prob")
+    else:
+        assert hp is None
