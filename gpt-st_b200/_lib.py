@@ -31,6 +31,8 @@ SIGNATURES = {
     "gptst_loss_parts": (_i, []),
     "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _f]),
+    "gptst_opt_chunk": (_i, []),
+    "gptst_adam_clip": (_i, [_f, _f, _i, _f, _f, _f, _f, _f]),
     "gptst_version": (C.c_char_p, []),
 }
 

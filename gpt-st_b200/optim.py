@@ -1,0 +1,89 @@
+"""Fused global-norm clipping + Adam (csrc/optim.cu): two kernel launches for the whole parameter set.
+
+Drop-in for the reference's ``clip_grad_norm_(model.parameters(), max_grad_norm); optimizer.step()``
+(BasicTrainer.py:94-97, Adam created at Run.py:134).  Parameters whose ``.grad`` is None are skipped exactly as
+torch.optim.Adam skips them, and their step count starts at their first gradient.  CUDA-graph safe: the pointer table
+travels through a pinned host buffer (a memcpy node that re-reads the same, still valid, addresses at replay).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+
+from . import _lib, ops
+
+
+class FusedAdamClip:
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 3e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 max_grad_norm: Optional[float] = 5.0):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedAdamClip needs CUDA parameters (no CPU fallback)")
+        self.device = dev
+        self.state = {}                                    # param -> (exp_avg, exp_avg_sq, first_step)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.host_steps = 0                                # mirror of step_count for assigning first_step
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, max_grad_norm if max_grad_norm else 0.0],
+                                  dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._tables = {}                                  # key -> [pinned table, dev table, dev block map, partial, nblocks, pinned map]
+        self._captures = 0
+        self.chunk = _lib.lib().gptst_opt_chunk()
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0:1].fill_(lr)
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def _table(self, live):
+        """(Re)build the pointer table for the current gradient tensors.  Inside a CUDA-graph capture this runs once:
+        the addresses are static across replays."""
+        rows, bmap = [], []
+        for idx, p in enumerate(live):
+            if p not in self.state:
+                self.state[p] = (torch.zeros_like(p, memory_format=torch.contiguous_format),
+                                 torch.zeros_like(p, memory_format=torch.contiguous_format), self.host_steps)
+            m, v, first = self.state[p]
+            g = p.grad
+            if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
+                raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
+            n = p.numel()
+            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, first])
+            bmap += [[idx, c] for c in range((n + self.chunk - 1) // self.chunk)]
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            self._captures += 1
+        key = (len(live), self._captures if capturing else 0)      # a captured graph owns its table (never rewritten later)
+        ent = self._tables.get(key)
+        if ent is None or ent[0].shape[0] != len(rows) or ent[4] != len(bmap):
+            pinned = torch.empty((len(rows), 6), dtype=torch.int64).pin_memory()
+            bpin = torch.tensor(bmap, dtype=torch.int32).pin_memory()
+            bdev = torch.empty((len(bmap), 2), dtype=torch.int32, device=self.device)
+            bdev.copy_(bpin, non_blocking=True)                     # pinned -> device: legal inside a capture
+            ent = [pinned, torch.empty((len(rows), 6), dtype=torch.int64, device=self.device), bdev,
+                   torch.empty(len(bmap), dtype=torch.float32, device=self.device), len(bmap), bpin]
+            self._tables[key] = ent
+        ent[0].copy_(torch.tensor(rows, dtype=torch.int64))
+        ent[1].copy_(ent[0], non_blocking=True)
+        return ent
+
+    def step(self) -> None:
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        ent = self._table(live)
+        self.host_steps += 1
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        ops._count(2)
+        _lib.check(L.gptst_adam_clip(ent[1].data_ptr(), ent[2].data_ptr(), ent[4], ent[3].data_ptr(), self.step_count.data_ptr(),
+                                     self.hyper.data_ptr(), self.norm.data_ptr(), st), "gptst_adam_clip")

@@ -26,14 +26,20 @@ from .losses import pretrain_loss_syncfree, probe_loss
 class PretrainStep:
     def __init__(self, model, lr: float = 3e-3, max_grad_norm: Optional[float] = 5.0, loss: Union[str, Callable] = "probe",
                  scaler_mean: float = 0.0, scaler_std: float = 1.0, use_graph: bool = True, reducer: Optional[_dp.FlatGradAllReduce] = None,
-                 optimizer: Optional[torch.optim.Optimizer] = None):
+                 optimizer: Optional[torch.optim.Optimizer] = None, fused_optimizer: bool = True):
         self.model = model
         self.enc = model.encoder
         self.max_grad_norm = max_grad_norm
         self.use_graph = use_graph
         self.reducer = reducer
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = optimizer or torch.optim.Adam(self.params, lr=lr, eps=1e-8, capturable=use_graph, foreach=True)
+        # graph mode: fused clip+Adam (two launches); eager mode / user-supplied optimiser: torch's foreach path
+        self.fused_opt = None
+        if optimizer is None and use_graph and fused_optimizer:
+            from .optim import FusedAdamClip
+            self.fused_opt = FusedAdamClip(self.params, lr=lr, eps=1e-8, max_grad_norm=max_grad_norm)
+        self.opt = optimizer or (None if self.fused_opt else torch.optim.Adam(self.params, lr=lr, eps=1e-8, capturable=use_graph,
+                                                                              foreach=True))
         if isinstance(loss, str):
             from . import ops as _ops
             if loss == "probe":
@@ -56,16 +62,23 @@ class PretrainStep:
         self.launches_per_step = 0
 
     # -- one eager step (also the body that gets captured) ------------------------------------------------
+    def _zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
     def _body(self, src, epoch):
-        self.opt.zero_grad(set_to_none=True)
+        self._zero_grad()
         outs = self.model(src, src, None, epoch)
         loss = self.loss_fn(outs, src, epoch)
         loss.backward()
         if self.reducer is not None:
             self.reducer.reduce()
-        if self.max_grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, foreach=True)
-        self.opt.step()
+        if self.fused_opt is not None:
+            self.fused_opt.step()                      # clip + Adam, two launches
+        else:
+            if self.max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, foreach=True)
+            self.opt.step()
         return loss.detach()
 
     def _phase(self, epoch):
@@ -81,7 +94,7 @@ class PretrainStep:
             plan_dev = self.enc.mask_plan(n, epoch).to(dev)
             self.enc.plan_override = plan_dev
         g = torch.cuda.CUDAGraph()
-        self.opt.zero_grad(set_to_none=True)
+        self._zero_grad()
         torch.cuda.synchronize()
         from . import ops as _ops
         l0 = _ops.launch_count()

@@ -84,6 +84,15 @@ int gptst_pretrain_loss(const float* o, const float* src, const long long* inv_m
                         float* d_o, float* d_prob, float* part, float* out, long n_cells, int ibd, int src_stride, int H,
                         int mode, float mean, float std_, float thr, float kl_w, void* stream);
 
+/* ---- fused global-norm clipping + Adam over a tensor list (BasicTrainer.py:94-97, Run.py:134) --------------
+ * table: device array of 6 x int64 per tensor {param ptr, grad ptr, exp_avg ptr, exp_avg_sq ptr, numel, first_step};
+ * block_map: device int2 per block {tensor index, chunk index} with gptst_opt_chunk() elements per chunk;
+ * partial: nblocks floats scratch; step: device int32 global step (incremented here); hyper: device float[5]
+ * {lr, beta1, beta2, eps, max_norm (<= 0 disables clipping)}; norm_out: optional device float (pre-clip grad norm).   */
+int gptst_opt_chunk(void);
+int gptst_adam_clip(const void* table, const void* block_map, int nblocks, float* partial, int* step, const float* hyper,
+                    float* norm_out, void* stream);
+
 /* library identification: "gptst_b200 <version> sm_100a" */
 const char* gptst_version(void);
 

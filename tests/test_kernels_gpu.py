@@ -257,3 +257,29 @@ def test_fused_loss_matches_reference_losses(mode, use_kl, ibd):
         check(hp, gp.double(), 1e-5, "fused loss d/d prob")
     else:
         assert hp is None
+
+
+def test_fused_adam_clip_matches_torch():
+    """clip_grad_norm_ + torch.optim.Adam vs the fused two-launch kernel pair, incl. a parameter whose first gradient
+    arrives late (its bias correction must restart at t=1) and a step where clipping is active."""
+    from gptst_b200.optim import FusedAdamClip
+    g = torch.Generator().manual_seed(9)
+    shapes = [(16, 64, 64), (64,), (170, 16), (4, 10, 170), (1, 64), (5000,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ref = torch.optim.Adam(pb, lr=3e-3, eps=1e-8)
+    opt = FusedAdamClip(pa, lr=3e-3, eps=1e-8, max_grad_norm=5.0)
+    for it in range(6):
+        scale = 30.0 if it % 2 == 0 else 0.01          # alternate clipped / unclipped steps
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 3 and it < 2:
+                a.grad = b.grad = None                  # late starter
+                continue
+            gr = torch.randn(a.shape, generator=g).cuda() * scale
+            a.grad, b.grad = gr.clone(), gr.clone()
+        torch.nn.utils.clip_grad_norm_(pb, 5.0)
+        ref.step()
+        opt.step()
+        for a, b in zip(pa, pb):
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (it, (a - b).abs().max().item())
+    assert int(opt.step_count.item()) == 6
