@@ -343,6 +343,11 @@ static cudaError_t launch_route_fwd(const float* x, const float* Wp, const float
     return cudaLaunchKernelEx(&cfg, kern, x, Wp, bp, dadj, c, s, N, H, R, cs, rpc);
 }
 
+// second generation (cap_route2_fwd.cu): D = 64, N <= 256, fp16-split tensor-core routing
+bool route2_supported(int N, int D, int H);
+cudaError_t route2_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int BT,
+                       int N, int H, int R, int prec, cudaStream_t st);
+
 }  // namespace gptst
 
 using namespace gptst;
@@ -352,6 +357,7 @@ extern "C" int gptst_cap_route_fwd(const float* x, const float* Wp, const float*
     if (!x || !Wp || !bp || !dadj || !c || !s || B <= 0 || T <= 0 || N <= 0 || R < 0) return -1;
     if (H < 1 || H > 15) return -2;
     cudaStream_t st = (cudaStream_t)stream;
+    if ((prec == 1 || prec == 3) && route2_supported(N, D, H)) return (int)route2_fwd(x, Wp, bp, dadj, c, s, B * T, N, H, R, prec, st);
     if (D == 64 && prec == 1) return (int)launch_route_fwd<64, 1>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     if (D == 64 && prec == 3) return (int)launch_route_fwd<64, 3>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     if (D == 128 && prec == 1) return (int)launch_route_fwd<128, 1>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);

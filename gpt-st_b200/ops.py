@@ -168,15 +168,17 @@ class _CapCore(torch.autograd.Function):
         H, HT = dadj.shape[2], dyn.shape[1]
         L = _lib.lib()
         st = _stream()
-        _count(2)  # route_fwd + hop_fwd + recon share `st`
+        _count(2)  # route_fwd + hop_e1 + recon_hop share `st`
         c = torch.empty((B, T, H, N), device=x.device, dtype=torch.float32)
         s = torch.empty((B, T, H, D), device=x.device, dtype=torch.float32)
         _lib.check(L.gptst_cap_route_fwd(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), B, T, N, D, H, int(num_route),
                                          prec, st), "gptst_cap_route_fwd")
         v = torch.empty_like(s)
-        _lib.check(L.gptst_cap_hop_fwd(_p(s), _p(dyn), _p(v), B, T, D, H, HT, st), "gptst_cap_hop_fwd")
+        e1 = torch.empty((B, HT, D), device=x.device, dtype=torch.float32)
         recon = torch.empty_like(x)
-        _lib.check(L.gptst_cap_recon(_p(c), _p(v), _p(recon), B, T, N, D, H, st), "gptst_cap_recon")
+        _lib.check(L.gptst_cap_hop_e1(_p(s), _p(dyn), _p(e1), B, T, D, H, HT, st), "gptst_cap_hop_e1")
+        _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
+                   "gptst_cap_recon_hop")
         out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
         ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out)
         ctx.prec = prec

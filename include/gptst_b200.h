@@ -52,13 +52,21 @@ int gptst_tmix_dM(const float* dy, const float* x, float* dM_part, int B, int T,
 
 /* ---- cap: intra-cluster routing, GPTST.py:102-123 ----------------------------------------------------
  * P = squash(x Wp^T + bp); R routing iterations on (P, dadj); c = softmax_H(b + dadj) -> c (B,T,H,N); s = c P.
- * One thread-block cluster per (b,t) slab; the cluster size is chosen so the slab's P tile stays in shared memory. */
+ * D = 64, N <= 256: one CTA per (b,t) slab, one warp per 16 nodes, fp16-split tensor-core contractions
+ * (cap_route2_fwd.cu).  Otherwise one thread-block cluster per slab, sized so the slab's P tile stays in shared memory
+ * (cap_route_fwd.cu, tf32 split).                                                                               */
 int gptst_cap_route_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int B,
                         int T, int N, int D, int H, int R, int prec, void* stream);
 /* ---- cap: inter-cluster hop over k=(t,h) per sample, GPTST.py:125-134:  v = squash(LReLU(dyn^T LReLU(dyn (s+tau))) + s) */
 int gptst_cap_hop_fwd(const float* s, const float* dyn, float* v, int B, int T, int D, int H, int HT, void* stream);
 /* ---- cap: hyperedge -> node reconstruction, GPTST.py:135:  recon[b,t,n,:] = sum_h c[b,t,h,n] v[b,t,h,:]      */
 int gptst_cap_recon(const float* c, const float* v, float* recon, int B, int T, int N, int D, int H, void* stream);
+/* ---- cap: the same two steps (GPTST.py:125-135) split for parallelism; this pair is what the forward path launches.
+ * hop_e1:    e1[b] = LReLU(dyn_b (s_b + tau)), e1 is (B, HT, D) -- the only part that mixes the T slabs of a sample.
+ * recon_hop: per slab  v = squash(LReLU(dyn_b[:, t-block]^T e1[b]) + s) -> v (B,T,H,D);  recon = c^T v -> (B,T,N,D).   */
+int gptst_cap_hop_e1(const float* s, const float* dyn, float* e1, int B, int T, int D, int H, int HT, void* stream);
+int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const float* e1, float* v, float* recon, int B,
+                        int T, int N, int D, int H, int HT, void* stream);
 /* ---- cap backward pieces ------------------------------------------------------
  * dv = c drecon, dcr = v drecon^T                                                                            */
 int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int B, int T, int N,
