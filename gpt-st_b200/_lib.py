@@ -28,6 +28,8 @@ SIGNATURES = {
     "gptst_cap_recon_hop": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_dv_dcr": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_hop_bwd_parts": (_i, [_i]),
+    "gptst_cap_hop_bwd2": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route_bwd_parts": (_i, [_i, _i, _i, _i, _i]),
     "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_loss_parts": (_i, []),

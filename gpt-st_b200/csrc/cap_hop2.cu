@@ -98,6 +98,115 @@ __global__ void __launch_bounds__(256) cap_recon_hop_kernel(const float* __restr
     }
 }
 
+
+// ---- backward of the hop, split the same way ---------------------------------------------
+//   hop_bwd_rows (per slab)        : recompute pre2 = dyn_b[:, t-block]^T E1 and r ; dr = squash'(r, dv) ; dpre2 = dr * phi'(pre2)
+//   hop_bwd_cols (per sample, 16 columns of D) : dE1 = dyn dpre2 ; dpre1 = dE1 * phi'(pre1) ; ds = dr + dyn^T dpre1 ;
+//                                    ddyn_part[chunk] = E1 dpre2^T + dpre1 (s+tau)^T  restricted to the chunk's columns
+template <int D>
+__global__ void __launch_bounds__(256) cap_hop_bwd_rows_kernel(const float* __restrict__ s, const float* __restrict__ dyn,
+                                                               const float* __restrict__ e1, const float* __restrict__ dv,
+                                                               float* __restrict__ dr_out, float* __restrict__ dpre2_out,
+                                                               int T, int H, int HT) {
+    extern __shared__ __align__(16) float smem[];
+    float* E1 = smem;                      // [HT][D]
+    float* dy = E1 + (size_t)HT * D;       // [HT][H]
+    const int slab = blockIdx.x, b = slab / T, tt = slab % T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = T * H;
+    for (int i = tid; i < HT * D / 4; i += 256)
+        reinterpret_cast<float4*>(E1)[i] = reinterpret_cast<const float4*>(e1 + (size_t)b * HT * D)[i];
+    for (int i = tid; i < HT * H; i += 256) dy[i] = dyn[((size_t)b * HT + i / H) * K + tt * H + (i % H)];
+    __syncthreads();
+    for (int h = warp; h < H; h += 8) {
+        float r[D / 32], g[D / 32], p2[D / 32];
+        float q = 0.f, rg = 0.f;
+        const size_t row = ((size_t)slab * H + h) * D;
+#pragma unroll
+        for (int j = 0; j < D / 32; ++j) {
+            const int d = lane + 32 * j;
+            float a = 0.f;
+            for (int ht = 0; ht < HT; ++ht) a = fmaf(dy[ht * H + h], E1[ht * D + d], a);
+            p2[j] = a;
+            r[j] = lrelu(a) + s[row + d];
+            g[j] = dv[row + d];
+            q += r[j] * r[j];
+            rg += r[j] * g[j];
+        }
+        q = warp_sum(q);
+        rg = warp_sum(rg);
+        const float f = squash_f(q), fp = squash_df(q);
+#pragma unroll
+        for (int j = 0; j < D / 32; ++j) {
+            const int d = lane + 32 * j;
+            const float dr = f * g[j] + 2.f * r[j] * fp * rg;
+            dr_out[row + d] = dr;
+            dpre2_out[row + d] = lrelu_grad(p2[j], dr);
+        }
+    }
+}
+
+// grid (B, D/16), 256 threads
+__global__ void __launch_bounds__(256) cap_hop_bwd_cols_kernel(const float* __restrict__ s, const float* __restrict__ dyn,
+                                                               const float* __restrict__ e1, const float* __restrict__ dr,
+                                                               const float* __restrict__ dpre2, float* __restrict__ ds,
+                                                               float* __restrict__ ddyn_part, int B, int T, int D, int H,
+                                                               int HT) {
+    extern __shared__ __align__(16) float smem[];
+    const int K = T * H, C = kE1Cols;
+    float* Ss = smem;                         // [K][C]   s + tau
+    float* P2 = Ss + (size_t)K * C;           // [K][C]   dpre2
+    float* E1 = P2 + (size_t)K * C;           // [HT][C]
+    float* D1 = E1 + (size_t)HT * C;          // [HT][C]  dpre1
+    float* dy = D1 + (size_t)HT * C;          // [HT][K+1]
+    const int tid = threadIdx.x, b = blockIdx.x, c0 = blockIdx.y * C;
+    for (int i = tid; i < K * (C / 4); i += 256) {
+        const int k = i / (C / 4), q = i % (C / 4);
+        const size_t off = ((size_t)b * K + k) * D + c0 + 4 * q;
+        float4 v = *reinterpret_cast<const float4*>(s + off);
+        const float tau = (float)(k / H + 1) / 12.f;
+        v.x += tau; v.y += tau; v.z += tau; v.w += tau;
+        *reinterpret_cast<float4*>(Ss + k * C + 4 * q) = v;
+        *reinterpret_cast<float4*>(P2 + k * C + 4 * q) = *reinterpret_cast<const float4*>(dpre2 + off);
+    }
+    for (int i = tid; i < HT * (C / 4); i += 256) {
+        const int ht = i / (C / 4), q = i % (C / 4);
+        *reinterpret_cast<float4*>(E1 + ht * C + 4 * q) = *reinterpret_cast<const float4*>(e1 + ((size_t)b * HT + ht) * D + c0 + 4 * q);
+    }
+    for (int i = tid; i < HT * K; i += 256) dy[(i / K) * (K + 1) + (i % K)] = dyn[(size_t)b * HT * K + i];
+    __syncthreads();
+    const int col = tid & (C - 1);
+    for (int ht = tid / C; ht < HT; ht += 256 / C) {
+        const float* drow = dy + ht * (K + 1);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int k = 0;
+        for (; k + 3 < K; k += 4) {
+            a0 = fmaf(drow[k], P2[k * C + col], a0);
+            a1 = fmaf(drow[k + 1], P2[(k + 1) * C + col], a1);
+            a2 = fmaf(drow[k + 2], P2[(k + 2) * C + col], a2);
+            a3 = fmaf(drow[k + 3], P2[(k + 3) * C + col], a3);
+        }
+        for (; k < K; ++k) a0 = fmaf(drow[k], P2[k * C + col], a0);
+        D1[ht * C + col] = lrelu_grad(E1[ht * C + col], (a0 + a1) + (a2 + a3));     // sign(E1) == sign(pre1)
+    }
+    __syncthreads();
+    for (int i = tid; i < K * C; i += 256) {
+        const int k = i / C, cc = i % C;
+        const size_t off = ((size_t)b * K + k) * D + c0 + cc;
+        float a = dr[off];
+        for (int ht = 0; ht < HT; ++ht) a = fmaf(dy[ht * (K + 1) + k], D1[ht * C + cc], a);
+        ds[off] = a;
+    }
+    float* dp = ddyn_part + ((size_t)blockIdx.y * B + b) * HT * K;
+    for (int i = tid; i < HT * K; i += 256) {
+        const int ht = i / K, k = i % K;
+        float a = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) a = fmaf(E1[ht * C + cc], P2[k * C + cc], fmaf(D1[ht * C + cc], Ss[k * C + cc], a));
+        dp[i] = a;
+    }
+}
+
 }  // namespace gptst
 
 using namespace gptst;
@@ -131,5 +240,29 @@ extern "C" int gptst_cap_recon_hop(const float* c, const float* s, const float* 
     if (D == 64) cap_recon_hop_kernel<64><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
     else if (D == 128) cap_recon_hop_kernel<128><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
     else return -2;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int gptst_cap_hop_bwd_parts(int D) { return D / kE1Cols; }
+
+// dr_tmp, dpre2_tmp: scratch (B,T,H,D) each; ddyn_part: (gptst_cap_hop_bwd_parts(D), B, HT, T*H), summed by the caller.
+extern "C" int gptst_cap_hop_bwd2(const float* s, const float* dyn, const float* e1, const float* dv, float* dr_tmp,
+                                  float* dpre2_tmp, float* ds, float* ddyn_part, int B, int T, int D, int H, int HT,
+                                  void* stream) {
+    if (!s || !dyn || !e1 || !dv || !dr_tmp || !dpre2_tmp || !ds || !ddyn_part || B <= 0 || T <= 0 || HT <= 0) return -1;
+    if (H < 1 || H > kMaxH || D % kE1Cols != 0) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = T * H;
+    const size_t smem1 = ((size_t)HT * D + (size_t)HT * H) * 4;
+    const size_t smem2 = ((size_t)2 * K * kE1Cols + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
+    if (smem1 > 48 * 1024 || smem2 > kSmemMax) return -2;
+    if (D == 64) cap_hop_bwd_rows_kernel<64><<<B * T, 256, smem1, st>>>(s, dyn, e1, dv, dr_tmp, dpre2_tmp, T, H, HT);
+    else if (D == 128) cap_hop_bwd_rows_kernel<128><<<B * T, 256, smem1, st>>>(s, dyn, e1, dv, dr_tmp, dpre2_tmp, T, H, HT);
+    else return -2;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(cap_hop_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    cap_hop_bwd_cols_kernel<<<dim3(B, D / kE1Cols), 256, smem2, st>>>(s, dyn, e1, dr_tmp, dpre2_tmp, ds, ddyn_part, B, T, D, H, HT);
     return (int)cudaGetLastError();
 }

@@ -18,68 +18,17 @@
 //   final   : b += v P^T ; c = softmax_H(b + dadj) -> c_out ; s = c P -> s_out
 // The logit MMA (M = 16 hyperedges, N = 8 nodes, K = D) leaves its result in exactly the A-fragment layout of the
 // aggregation MMA (M = 16 hyperedges, N = 8 columns of D, K = 16 nodes), so softmax outputs never leave registers.
-#include <cuda_fp16.h>
-
 #include <cstdlib>
 
 #include "cap_common.cuh"
+#include "mma_f16.cuh"
 
 namespace gptst {
 namespace r2 {
 
+using namespace hf;
 constexpr int D = 64;
-constexpr int ROWB = 272;     // bytes per shared-memory row: [0,128) hi plane (64 halves) | [128,256) lo plane | 16 pad
-constexpr int LO = 128;       // byte offset of the lo plane inside a row
-constexpr int REDLD = 72;     // floats per row of the cross-warp partial buffer (conflict-free float2 stores)
 constexpr float WSCALE = 64.f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
-}
-// D(16x8, f32) += A(16x16, f16, row) * B(16x8, f16, col)
-//   A regs: 0=(row g, k 2t..2t+1) 1=(row g+8, same k) 2=(row g, k 2t+8..2t+9) 3=(row g+8, k 2t+8..)     g = lane>>2, t = lane&3
-//   B regs: b0=(k 2t..2t+1, n g)  b1=(k 2t+8..2t+9, n g)          C: 0=(g,2t) 1=(g,2t+1) 2=(g+8,2t) 3=(g+8,2t+1)
-__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-template <int PREC>
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
-                                     uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-    if (PREC == PREC_3XTF32) {
-        mma_f16(c, al, bh0, bh1);
-        mma_f16(c, ah, bl0, bl1);
-    }
-    mma_f16(c, ah, bh0, bh1);
-}
-// (a, b) -> packed fp16 pair hi and the packed residual lo
-template <int PREC>
-__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    if (PREC == PREC_3XTF32) {
-        const float2 f = __half22float2(h);
-        const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
-        lo = *reinterpret_cast<const uint32_t*>(&l);
-    } else {
-        lo = 0u;
-    }
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
 __host__ __device__ inline size_t wred_bytes(int NW, int H) {
     const size_t w = (size_t)D * ROWB, r = (size_t)NW * (H + 1) * REDLD * 4;
@@ -234,64 +183,9 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
 #pragma unroll
     for (int i = 0; i < 8; ++i) bl[i] = 0.f;
 
-    // logits: z += v P^T over this warp's 16 nodes  (A = v planes, B = P rows; two accumulators per tile)
-    auto add_logits = [&](float (&z)[8]) {
-        float zh[2][4], zl[2][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) zh[0][i] = zh[1][i] = zl[0][i] = zl[1][i] = 0.f;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            uint32_t vh[4], vl[4] = {0u, 0u, 0u, 0u}, ph[4], pl[4] = {0u, 0u, 0u, 0u};
-            const uint32_t aaddr = smem_u32(vpl + (size_t)(8 * ((lane >> 3) & 1) + (lane & 7)) * ROWB + (16 * b + 8 * (lane >> 4)) * 2);
-            const uint32_t baddr =
-                smem_u32(Prow + (size_t)(n0 + 8 * (lane >> 4) + (lane & 7)) * ROWB + (16 * b + 8 * ((lane >> 3) & 1)) * 2);
-            ldsm_x4(vh, aaddr);
-            ldsm_x4(ph, baddr);
-            if (PREC == PREC_3XTF32) {
-                ldsm_x4(vl, aaddr + LO);
-                ldsm_x4(pl, baddr + LO);
-                mma_f16(zl[0], vl, ph[0], ph[1]);
-                mma_f16(zl[1], vl, ph[2], ph[3]);
-                mma_f16(zl[0], vh, pl[0], pl[1]);
-                mma_f16(zl[1], vh, pl[2], pl[3]);
-            }
-            mma_f16(zh[0], vh, ph[0], ph[1]);
-            mma_f16(zh[1], vh, ph[2], ph[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            z[i] += zh[0][i] + zl[0][i];
-            z[4 + i] += zh[1][i] + zl[1][i];
-        }
-    };
-    // aggregation: red[warp][h][:] = sum over this warp's 16 nodes of c[h][n] P[n][:]   (rows h < HA)
+    auto add_logits = [&](float (&z)[8]) { warp_logits<PREC>(z, vpl, Prow, n0, lane, 1.f); };
     auto aggregate = [&](const float (&c)[8], int HA) {
-        uint32_t ah[4], al[4];
-        split_h2<PREC>(c[0], c[1], ah[0], al[0]);
-        split_h2<PREC>(c[2], c[3], ah[1], al[1]);
-        split_h2<PREC>(c[4], c[5], ah[2], al[2]);
-        split_h2<PREC>(c[6], c[7], ah[3], al[3]);
-        float* r0 = red + ((size_t)warp * (H + 1) + h0) * REDLD + 2 * t;
-        float* r1 = red + ((size_t)warp * (H + 1) + h1) * REDLD + 2 * t;
-#pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
-            uint32_t bh[4], bq[4] = {0u, 0u, 0u, 0u};
-            const uint32_t baddr =
-                smem_u32(Prow + (size_t)(n0 + 8 * ((lane >> 3) & 1) + (lane & 7)) * ROWB + (16 * jp + 8 * (lane >> 4)) * 2);
-            ldsm_x4_t(bh, baddr);
-            if (PREC == PREC_3XTF32) ldsm_x4_t(bq, baddr + LO);
-            float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma3<PREC>(a0, ah, al, bh[0], bh[1], bq[0], bq[1]);
-            mma3<PREC>(a1, ah, al, bh[2], bh[3], bq[2], bq[3]);
-            if (h0 < HA) {
-                *reinterpret_cast<float2*>(r0 + 16 * jp) = make_float2(a0[0], a0[1]);
-                *reinterpret_cast<float2*>(r0 + 16 * jp + 8) = make_float2(a1[0], a1[1]);
-            }
-            if (h1 < HA) {
-                *reinterpret_cast<float2*>(r1 + 16 * jp) = make_float2(a0[2], a0[3]);
-                *reinterpret_cast<float2*>(r1 + 16 * jp + 8) = make_float2(a1[2], a1[3]);
-            }
-        }
+        warp_aggregate<PREC>(c, HA, Prow, n0, red + (size_t)warp * (H + 1) * REDLD, lane, 1.f);
     };
     // cross-warp sum of one row of the partials (deterministic order); lane owns columns 2*lane, 2*lane+1
     auto row_total = [&](int h) {

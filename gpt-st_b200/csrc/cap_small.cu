@@ -220,6 +220,10 @@ __global__ void __launch_bounds__(256) cap_dv_dcr_kernel(const float* __restrict
     }
 }
 
+bool route2_supported(int N, int D, int H);   // cap_route2_fwd.cu
+cudaError_t dv_dcr2(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int BT, int N, int H,
+                    cudaStream_t st);         // cap_dvdcr2.cu
+
 }  // namespace gptst
 
 using namespace gptst;
@@ -288,6 +292,7 @@ extern "C" int gptst_cap_dv_dcr(const float* c, const float* v, const float* dre
     if (!c || !v || !drecon || !dv || !dcr || B <= 0 || N <= 0) return -1;
     if (H > kMaxH) return -2;
     cudaStream_t st = (cudaStream_t)stream;
+    if (route2_supported(N, D, H)) return (int)dv_dcr2(c, v, drecon, dv, dcr, B * T, N, H, st);
     const int nlanes = 256 / (D / 4);
     size_t smem = ((size_t)kMaxH * D + (size_t)nlanes * H * D) * 4;
     cudaError_t e;

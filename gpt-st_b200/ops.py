@@ -180,27 +180,30 @@ class _CapCore(torch.autograd.Function):
         _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
                    "gptst_cap_recon_hop")
         out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
-        ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out)
+        ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1)
         ctx.prec = prec
         ctx.mark_non_differentiable(c)
         return out, c
 
     @staticmethod
     def backward(ctx, dout, _dc):
-        x, Wp, bp, dyn, Wn, c, s, v, recon, out = ctx.saved_tensors
+        x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1 = ctx.saved_tensors
         B, T, N, D = x.shape
         H, HT = c.shape[2], dyn.shape[1]
         L = _lib.lib()
         st = _stream()
-        _count(2)  # dv_dcr + hop_bwd + route_bwd share `st`
+        _count(3)  # dv_dcr + hop_bwd2 (two launches) + route_bwd share `st`
         dout = dout.contiguous()
         drecon, dWn, dbn, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True)
         dv = torch.empty_like(s)
         dcr = torch.empty_like(c)
         _lib.check(L.gptst_cap_dv_dcr(_p(c), _p(v), _p(drecon), _p(dv), _p(dcr), B, T, N, D, H, st), "gptst_cap_dv_dcr")
         ds = torch.empty_like(s)
-        ddyn = torch.empty_like(dyn)
-        _lib.check(L.gptst_cap_hop_bwd(_p(s), _p(dyn), _p(dv), _p(ds), _p(ddyn), B, T, D, H, HT, st), "gptst_cap_hop_bwd")
+        dr_tmp, dp2_tmp = torch.empty_like(s), torch.empty_like(s)
+        ddyn_part = torch.empty((L.gptst_cap_hop_bwd_parts(D),) + tuple(dyn.shape), device=x.device, dtype=torch.float32)
+        _lib.check(L.gptst_cap_hop_bwd2(_p(s), _p(dyn), _p(e1), _p(dv), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D,
+                                        H, HT, st), "gptst_cap_hop_bwd2")
+        ddyn = ddyn_part.sum(0)
         parts = L.gptst_cap_route_bwd_parts(B, T, N, D, H)
         dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)
         dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)

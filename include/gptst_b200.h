@@ -74,6 +74,11 @@ int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float*
 /* dv -> ds (B,T,H,D) and ddyn (B,HT,T*H)                                                                      */
 int gptst_cap_hop_bwd(const float* s, const float* dyn, const float* dv, float* ds, float* ddyn, int B, int T, int D,
                       int H, int HT, void* stream);
+/* the same, split for parallelism (per-slab row pass + per-(sample, 16-column) pass); e1 is the tensor hop_e1 wrote in
+ * forward; dr_tmp / dpre2_tmp are (B,T,H,D) scratch; ddyn_part is (gptst_cap_hop_bwd_parts(D), B, HT, T*H), the caller sums it. */
+int gptst_cap_hop_bwd_parts(int D);
+int gptst_cap_hop_bwd2(const float* s, const float* dyn, const float* e1, const float* dv, float* dr_tmp, float* dpre2_tmp,
+                       float* ds, float* ddyn_part, int B, int T, int D, int H, int HT, void* stream);
 /* dx_io holds dy = dOut*act'(out) on entry and dy + dZ Wp on exit; ddadj (B,T,H,N);
  * dWp_part (parts,D,D) [out][in], dbp_part (parts,D) with parts = gptst_cap_route_bwd_parts(...)              */
 int gptst_cap_route_bwd_parts(int B, int T, int N, int D, int H);
