@@ -32,6 +32,10 @@ SIGNATURES = {
     "gptst_cap_hop_bwd2": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route_bwd_parts": (_i, [_i, _i, _i, _i, _i]),
     "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_route2_supported": (_i, [_i, _i, _i]),
+    "gptst_cap_route_bwd_dz": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_linear_bwd_acc_splits": (_i, [_l, _i]),
+    "gptst_linear_bwd_acc": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
     "gptst_loss_parts": (_i, []),
     "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _f]),

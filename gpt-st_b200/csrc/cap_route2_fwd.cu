@@ -84,25 +84,7 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
         if (r < N) cp_async16(dst, xs + (size_t)r * D + ch * 4);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // The A operand of the Z product is fetched with ldmatrix from fp32 rows: matrix i of an x4 load is the 8 x 4-float
-    // block at columns 16b+4i, so lane (g,t) receives x[g][16b+4i+t].  The MMA's logical k index is therefore a
-    // permutation of the physical one inside every 16-block: logical {2t, 2t+1, 2t+8, 2t+9} <-> physical {t, 4+t, 8+t, 12+t};
-    // Wp is stored with the same permutation, so the contraction is unchanged.
-    for (int i = tid; i < D * 16; i += NT) {
-        const int o = i >> 4, q4 = i & 15;
-        const float4 w = *reinterpret_cast<const float4*>(Wp + (size_t)o * D + q4 * 4);
-        const int q = q4 & 3;
-        const int base = 16 * (q4 >> 2) + ((q >= 2) ? 8 : 0) + (q & 1);
-        const float wv[4] = {w.x * WSCALE, w.y * WSCALE, w.z * WSCALE, w.w * WSCALE};
-        __half* hrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB);
-        __half* lrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB + LO);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const __half h = __float2half_rn(wv[e]);
-            hrow[base + 2 * e] = h;
-            lrow[base + 2 * e] = __float2half_rn(wv[e] - __half2float(h));
-        }
-    }
+    stage_w_perm<PREC>(Wt, Wp, WSCALE, tid, NT);
     for (int i = tid; i < D; i += NT) bps[i] = bp[i];
     for (int i = tid; i < 16 * ROWB / 16; i += NT) reinterpret_cast<float4*>(vpl)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -128,29 +110,7 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
     // ---- Z = x Wp^T + bp ; P = squash(Z) -> hi/lo planes, in place over the warp's own x rows
     {
         float acc[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            uint32_t f[4], ah[4], al[4];
-            const uint32_t aaddr = smem_u32(Prow + (size_t)(n0 + (lane & 7)) * ROWB + (16 * b + 4 * (lane >> 3)) * 4);
-            ldsm_x4(f, aaddr);                       // rows n0..n0+7
-            split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[0], al[0]);
-            split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[2], al[2]);
-            ldsm_x4(f, aaddr + 8 * ROWB);            // rows n0+8..n0+15
-            split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[1], al[1]);
-            split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[3], al[3]);
-#pragma unroll
-            for (int jp = 0; jp < 4; ++jp) {
-                uint32_t bh[4], bl[4] = {0u, 0u, 0u, 0u};
-                const uint32_t baddr =
-                    smem_u32(Wt + (size_t)(16 * jp + 8 * (lane >> 4) + (lane & 7)) * ROWB + (16 * b + 8 * ((lane >> 3) & 1)) * 2);
-                ldsm_x4(bh, baddr);
-                if (PREC == PREC_3XTF32) ldsm_x4(bl, baddr + LO);
-                mma3<PREC>(acc[2 * jp], ah, al, bh[0], bh[1], bl[0], bl[1]);
-                mma3<PREC>(acc[2 * jp + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
-            }
-        }
+        warp_xw_tile<PREC>(acc, Prow, Wt, n0, lane);
         const int ra = n0 + g, rb = ra + 8;
         float q0 = 0.f, q1 = 0.f;
         constexpr float inv_scale = 1.f / WSCALE;

@@ -234,14 +234,6 @@ using namespace gptst;
     do {                                                                            \
         if ((H_) == 10) {                                                           \
             if ((D_) == 64 && (P_) == 1) { CALL(64, 1, 10); }                       \
-}  // namespace gptst
-
-using namespace gptst;
-
-#define CAP_DISPATCH(D_, P_, H_, CALL)                                              \
-    do {                                                                            \
-        if ((H_) == 10) {                                                           \
-            if ((D_) == 64 && (P_) == 1) { CALL(64, 1, 10); }                       \
             else if ((D_) == 64 && (P_) == 3) { CALL(64, 3, 10); }                  \
             else if ((D_) == 128 && (P_) == 1) { CALL(128, 1, 10); }                \
             else if ((D_) == 128 && (P_) == 3) { CALL(128, 3, 10); }                \

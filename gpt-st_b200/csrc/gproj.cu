@@ -275,14 +275,23 @@ cudaError_t gproj_fwd_umma(const float* X, const float* W, const float* bias, co
                            long gs, long rs, int act, int prec, cudaStream_t st);
 cudaError_t gproj_bwd_umma(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,
                            float* dRes, int G, int R, long gs, long rs, int act, int prec, int splits, cudaStream_t st);
-static bool use_umma() {
+// second generation for D = 64 (gproj2.cu): fp16-split mma.sync m16n8k16, forward and backward
+int gproj2_splits(int G, int R);
+cudaError_t gproj2_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R, long gs,
+                       long rs, int act, int prec, cudaStream_t st);
+cudaError_t gproj2_bwd(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,
+                       float* dRes, int G, int R, long gs, long rs, int act, int prec, int splits, int flags, cudaStream_t st);
+// GPTST_B200_GPROJ = "umma" (tcgen05 forward) | "mma" (first-generation tf32 mma.sync) select the older kernels (A/B testing)
+static int gproj_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GPTST_B200_GPROJ");
-        v = (e && e[0] == 'm') ? 0 : 1;   // GPTST_B200_GPROJ=mma selects the legacy mma.sync kernel (A/B testing)
+        v = (e && e[0] == 'm') ? 0 : (e && e[0] == 'u') ? 1 : 2;
     }
-    return v == 1;
+    return v;
 }
+static bool use_umma() { return gproj_impl() == 1; }
+static bool use_gp2(int D, int prec) { return gproj_impl() == 2 && D == 64 && (prec == 1 || prec == 3); }
 // The tcgen05(dX)+mma.sync(dW) backward is correct but (one CTA per SM, serial phases) still a little slower than the
 // two-CTA mma.sync kernel on PEMS08 shapes; opt-in with GPTST_B200_GPROJ_BWD=umma until it is pipelined.
 static bool use_umma_bwd() {
@@ -309,6 +318,7 @@ using namespace gptst;
     } while (0)
 
 extern "C" int gptst_gproj_splits(int G, int R, int D) {
+    if (use_gp2(D, 3)) return gproj2_splits(G, R);
     // enough CTAs to fill 148 SMs ~twice, never more than the number of row tiles
     int bm = (D <= 64) ? 128 : 64;
     int ntiles = (R + bm - 1) / bm;
@@ -321,6 +331,7 @@ extern "C" int gptst_gproj_fwd(const float* X, const float* W, const float* bias
                                int R, long group_stride, long row_stride, int D, int act, int prec, void* stream) {
     if (!X || !W || !Y || G <= 0 || R <= 0) return -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_gp2(D, prec)) return (int)gproj2_fwd(X, W, bias, Res, Y, G, R, group_stride, row_stride, act, prec, st);
     if (D == 64 && (prec == 1 || prec == 3) && use_umma())
         return (int)gproj_fwd_umma(X, W, bias, Res, Y, G, R, group_stride, row_stride, act, prec, st);
     int splits = gptst_gproj_splits(G, R, D);
@@ -336,6 +347,8 @@ extern "C" int gptst_gproj_bwd(const float* dY, const float* Y, const float* X, 
     if (!dY || !X || !W || !dX || !dW_part || !dbias_part || G <= 0 || R <= 0 || splits <= 0) return -1;
     if (act && !Y) return -1;
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_gp2(D, prec))
+        return (int)gproj2_bwd(dY, Y, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride, act, prec, splits, 0, st);
     if (D == 64 && (prec == 1 || prec == 3) && use_umma_bwd())
         return (int)gproj_bwd_umma(dY, Y, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride, act, prec, splits, st);
 #define CALL(DD, PP) \

@@ -148,5 +148,63 @@ __device__ __forceinline__ float2 pow2_scale_for_fp16(float m) {
     return make_float2(__int_as_float((127 + sh) << 23), __int_as_float((127 - sh) << 23));
 }
 
+
+// ---- x W^T for a 16-row tile with the A operand fetched by ldmatrix straight from fp32 rows ------------------------
+// Matrix i of an x4 load is the 8 x 4-float block at columns 16b+4i, so lane (g,t) receives x[g][16b+4i+t]: the MMA's
+// logical k index is a permutation of the physical one inside every 16-block,
+//     logical {2t, 2t+1, 2t+8, 2t+9}  <->  physical {t, 4+t, 8+t, 12+t},
+// and the weight is staged with the same permutation, so the contraction is unchanged.
+// stage_w_perm: W (64 x 64 fp32, [out][in] as nn.Linear stores it) * scale -> Wt rows = out, hi|lo planes along permuted in.
+template <int PREC>
+__device__ __forceinline__ void stage_w_perm(unsigned char* Wt, const float* __restrict__ W, float scale, int tid, int nthreads) {
+    for (int i = tid; i < 64 * 16; i += nthreads) {
+        const int o = i >> 4, q4 = i & 15;
+        const float4 w = *reinterpret_cast<const float4*>(W + (size_t)o * 64 + q4 * 4);
+        const int q = q4 & 3;
+        const int base = 16 * (q4 >> 2) + ((q >= 2) ? 8 : 0) + (q & 1);
+        const float wv[4] = {w.x * scale, w.y * scale, w.z * scale, w.w * scale};
+        __half* hrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB);
+        __half* lrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB + LO);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __half h = __float2half_rn(wv[e]);
+            hrow[base + 2 * e] = h;
+            lrow[base + 2 * e] = (PREC == PREC_3XTF32) ? __float2half_rn(wv[e] - __half2float(h)) : __float2half_rn(0.f);
+        }
+    }
+}
+// physical column of the permuted position p (inverse of the staging permutation)
+__device__ __forceinline__ int perm_pos_to_col(int p) {
+    const int b = p & ~15, r = p & 15;
+    return b + ((r & 8) ? 8 : 0) + ((r & 1) ? 4 : 0) + ((r & 7) >> 1);
+}
+// acc[j] (j = 8 column tiles of 8) = rows[n0..n0+15] (fp32) * Wt^T   (scaled by the staging scale)
+template <int PREC>
+__device__ __forceinline__ void warp_xw_tile(float (&acc)[8][4], const unsigned char* rows, const unsigned char* Wt, int n0, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        uint32_t f[4], ah[4], al[4];
+        const uint32_t aaddr = smem_u32(rows + (size_t)(n0 + (lane & 7)) * ROWB + (16 * b + 4 * (lane >> 3)) * 4);
+        ldsm_x4(f, aaddr);                       // rows n0..n0+7
+        split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[0], al[0]);
+        split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[2], al[2]);
+        ldsm_x4(f, aaddr + 8 * ROWB);            // rows n0+8..n0+15
+        split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[1], al[1]);
+        split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[3], al[3]);
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+            uint32_t bh[4], bl[4] = {0u, 0u, 0u, 0u};
+            const uint32_t baddr =
+                smem_u32(Wt + (size_t)(16 * jp + 8 * (lane >> 4) + (lane & 7)) * ROWB + (16 * b + 8 * ((lane >> 3) & 1)) * 2);
+            ldsm_x4(bh, baddr);
+            if (PREC == PREC_3XTF32) ldsm_x4(bl, baddr + LO);
+            mma3<PREC>(acc[2 * jp], ah, al, bh[0], bh[1], bl[0], bl[1]);
+            mma3<PREC>(acc[2 * jp + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
+        }
+    }
+}
+
 }  // namespace hf
 }  // namespace gptst

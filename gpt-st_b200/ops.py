@@ -204,12 +204,25 @@ class _CapCore(torch.autograd.Function):
         _lib.check(L.gptst_cap_hop_bwd2(_p(s), _p(dyn), _p(e1), _p(dv), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D,
                                         H, HT, st), "gptst_cap_hop_bwd2")
         ddyn = ddyn_part.sum(0)
-        parts = L.gptst_cap_route_bwd_parts(B, T, N, D, H)
-        dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)
-        dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
         ddadj = torch.empty_like(c)
-        _lib.check(L.gptst_cap_route_bwd(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dx), _p(ddadj), _p(dWp_part),
-                                         _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
+        if L.gptst_cap_route2_supported(N, D, H):
+            # second generation: dZ per slab, then the shared-weight contractions as one linear-layer backward
+            dZ = torch.empty_like(x)
+            _lib.check(L.gptst_cap_route_bwd_dz(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dZ), _p(ddadj), B, T, N, D, H,
+                                                ctx.prec, st), "gptst_cap_route_bwd_dz")
+            rows = B * T * N
+            parts = L.gptst_linear_bwd_acc_splits(rows, D)
+            dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)
+            dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
+            _count(1)
+            _lib.check(L.gptst_linear_bwd_acc(_p(dZ), _p(x), _p(Wp), _p(dx), _p(dWp_part), _p(dbp_part), rows, D, ctx.prec, parts,
+                                              st), "gptst_linear_bwd_acc")
+        else:
+            parts = L.gptst_cap_route_bwd_parts(B, T, N, D, H)
+            dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)
+            dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
+            _lib.check(L.gptst_cap_route_bwd(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dx), _p(ddadj), _p(dWp_part),
+                                             _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
         return dx, dWp_part.sum(0), dbp_part.sum(0), ddadj, ddyn, dWn, dbn, None, None
 
 

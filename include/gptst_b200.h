@@ -86,6 +86,19 @@ int gptst_cap_route_bwd(const float* x, const float* Wp, const float* bp, const 
                         const float* dcr, float* dx_io, float* ddadj, float* dWp_part, float* dbp_part, int B, int T,
                         int N, int D, int H, int prec, void* stream);
 
+/* ---- cap backward through the routing block, second generation (D = 64, N <= 256; gptst_cap_route2_supported tells) ---
+ * route_bwd_dz: recompute Z = x Wp^T + bp, P = squash(Z); dc = dcr + ds P^T; ddadj = c*(dc - sum_h c dc); dP = c^T ds;
+ *               dZ = squash'(Z, dP) -> dZ (B,T,N,D).  The two contractions with the shared weight follow as
+ * linear_bwd_acc: dX_io += dY W ; dW_part[s] = partial dY^T X ([out][in]) ; db_part[s] = partial sum dY, on (rows, D)
+ *               row-major operands; splits = gptst_linear_bwd_acc_splits(rows, D) partials, summed by the caller.      */
+int gptst_cap_route2_supported(int N, int D, int H);
+int gptst_cap_route_bwd_dz(const float* x, const float* Wp, const float* bp, const float* c, const float* ds,
+                           const float* dcr, float* dZ, float* ddadj, int B, int T, int N, int D, int H, int prec,
+                           void* stream);
+int gptst_linear_bwd_acc_splits(long rows, int D);
+int gptst_linear_bwd_acc(const float* dY, const float* X, const float* W, float* dX_io, float* dW_part, float* db_part,
+                         long rows, int D, int prec, int splits, void* stream);
+
 /* ---- fused pre-training loss + analytic gradients ------------------------------------
  * mode 0: probe loss mean|(o - x)*m| ; mode 1: masked MAE of Run.py:91-101 / lib/metrics.py:11-18 (inverse z-score with
  * mean/std, keep true*m > thr) ; plus kl_w * KLDivLoss(sum)(log prob, hs) (BasicTrainer.py:84-86) when kl_w != 0.
