@@ -306,7 +306,8 @@ class Hypergraph_encoder(nn.Module):
         else:
             plan = self.mask_plan(n, epoch).to(dev)
         order, ada, rnd = plan[:H], plan[H], plan[H + 1]
-        counts = torch.zeros(H, dtype=torch.int64, device=dev).scatter_add_(0, flat, torch.ones_like(flat))
+        # class histogram without atomics (scatter_add_ of 130k ones into 10 bins serialises: 68 us on a B200)
+        counts = (flat.unsqueeze(1) == torch.arange(H, device=dev)).sum(0)
         co = counts[order]
         picked = (torch.cumsum(co, 0) - co) < ada           # classes the reference's while-loop would add
         npick = picked.sum()

@@ -21,6 +21,8 @@ SIGNATURES = {
     "gptst_tmix": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_tmix_dM_splits": (_i, [_i, _i]),
     "gptst_tmix_dM": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_tmix_bwd_splits": (_i, [_i, _i]),
+    "gptst_tmix_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_fwd": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),

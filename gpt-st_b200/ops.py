@@ -115,6 +115,19 @@ def tmix(x, M, out=None, *, transpose=False, accumulate=False):
     return out
 
 
+def tmix_bwd(dy, x, M, dx_io, prec):
+    """Fused backward of the mix (D = 64): dx_io += M^T o dy (in place) and returns dM."""
+    B, T, N, D = x.shape
+    dy, x, M = _c(dy), _c(x), _c(M)
+    _chk(dy, x, M, dx_io)
+    L = _lib.lib()
+    splits = L.gptst_tmix_bwd_splits(B, N)
+    part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
+    rc = L.gptst_tmix_bwd(_p(dy), _p(x), _p(M), _p(dx_io), _p(part), B, T, N, D, prec, splits, _stream())
+    _lib.check(rc, "gptst_tmix_bwd")
+    return part[0] if splits == 1 else part.sum(0)
+
+
 def tmix_dM(dy, x):
     B, T, N, D = x.shape
     dy, x = _c(dy), _c(x)
@@ -145,9 +158,12 @@ class _HyperTemCore(torch.autograd.Function):
         eb, Mn, W, ret, out = ctx.saved_tensors
         dout = dout.contiguous()
         dret, dW, db, deb = gproj_bwd(dout, out, ret, W, node_grouped=False, act=True, prec=ctx.prec, want_dres=True)
-        tmix(dret, Mn, deb, transpose=True, accumulate=True)
-        dM = tmix_dM(dret, eb)
         B, T, N, D = eb.shape
+        if D == 64:
+            dM = tmix_bwd(dret, eb, Mn, deb, ctx.prec)
+        else:
+            tmix(dret, Mn, deb, transpose=True, accumulate=True)
+            dM = tmix_dM(dret, eb)
         return deb, dM, dW.view(B, T, D, D), db.view(B, T, D), None
 
 

@@ -50,6 +50,12 @@ int gptst_tmix(const float* x, const float* M, float* y, int B, int T, int N, in
 int gptst_tmix_dM_splits(int B, int N);
 int gptst_tmix_dM(const float* dy, const float* x, float* dM_part, int B, int T, int N, int D, int splits, void* stream);
 
+/* backward of the mix, fused (D = 64): dx_io[b,s,n,:] += sum_t M[n][t][s] dy[b,t,n,:]  and  dM_part[p][n][t][s] = partial over the
+ * batch range p of sum_{b,j} dy[b,t,n,j] x[b,s,n,j]; p < gptst_tmix_bwd_splits(B, N), summed by the caller.                 */
+int gptst_tmix_bwd_splits(int B, int N);
+int gptst_tmix_bwd(const float* dy, const float* x, const float* M, float* dx_io, float* dM_part, int B, int T, int N, int D,
+                   int prec, int splits, void* stream);
+
 /* ---- cap: intra-cluster routing, GPTST.py:102-123 ----------------------------------------------------
  * P = squash(x Wp^T + bp); R routing iterations on (P, dadj); c = softmax_H(b + dadj) -> c (B,T,H,N); s = c P.
  * D = 64, N <= 256: one CTA per (b,t) slab, one warp per 16 nodes, fp16-split tensor-core contractions
