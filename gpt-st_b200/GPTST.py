@@ -265,6 +265,7 @@ class Hypergraph_encoder(nn.Module):
         self.label_c_override = None
         # graph replay hook: int64 device vector [order, adaptive_num, random_num] (see mask_plan)
         self.plan_override = None
+        self._k_cache = {}
 
     # -- mask scorer (both phases), ref :326-332 / :338-343
     def _scores(self, source):
@@ -293,6 +294,25 @@ class Hypergraph_encoder(nn.Module):
         last class sub-sampled, then an exact-count random fill.  Restated without host synchronisation: the class
         selection loop of the reference (one `torch.sum(...)` D2H per class) becomes a 10-element prefix sum on the
         device, and `order[:k]` with a device-side k becomes a scatter of (rank >= k).  Same draws, same sorts."""
+        i0, H = self.input_base_dim, self.HS
+        dev = prob.device
+        if not prob.is_cuda:                         # host-side unit tests of the mask logic (the model itself is CUDA-only)
+            return self._adaptive_mask_torch(source, prob, epoch)
+        n = prob.numel() // H
+        if self.plan_override is not None:           # graph replay: a static device buffer refreshed by the caller
+            plan = self.plan_override
+        else:
+            plan = self.mask_plan(n, epoch).to(dev)
+        # the same two draws, in the same order, as the reference (:389, :400)
+        u1 = torch.rand_like(source[..., 0:1].reshape(-1))
+        u2 = torch.rand_like(source[..., 0:1].reshape(-1))
+        # label = arg-max class (== sort(descending)[..., 0] of ref :344-345 up to exact ties) unless a test injects labels
+        final = ops.mask_adaptive(prob, self.label_c_override, plan, u1, u2, i0, self.ada_type == "all")
+        return final.reshape(prob.shape[:-1] + (i0,))
+
+    def _adaptive_mask_torch(self, source, prob, epoch):
+        """The same mask with torch ops only (the sort-based restatement the kernels replace); kept as the readable
+        specification and used by the parity tests."""
         i0, H = self.input_base_dim, self.HS
         if self.label_c_override is not None:
             label_c = self.label_c_override
@@ -346,7 +366,13 @@ class Hypergraph_encoder(nn.Module):
         score = pro.get("score") if pro is not None else None     # (prob, event) computed on a side stream
         if epoch <= self.change_epoch:
             u = torch.rand_like(flow.reshape(-1))
-            final_mask = _exact_count_mask(u, int(u.shape[0] * self.mask_ratio))
+            k = int(u.shape[0] * self.mask_ratio)
+            kd = self._k_cache.get((k, u.device))
+            if kd is None:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("first use of a mask budget inside a CUDA-graph capture: run one eager step first")
+                kd = self._k_cache[(k, u.device)] = torch.tensor([k], dtype=torch.int64, device=u.device)
+            final_mask = ops.mask_random(u, kd)
             final_mask = final_mask.reshape(-1, self.horizon, self.num_node, i0)
             if score is None:
                 prob = self._scores(source)

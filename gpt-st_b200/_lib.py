@@ -38,6 +38,11 @@ SIGNATURES = {
     "gptst_cap_route_bwd_dz": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_linear_bwd_acc_splits": (_i, [_l, _i]),
     "gptst_linear_bwd_acc": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
+    "gptst_mask_labels": (_i, [_f, _f, _f, _l, _i, _f]),
+    "gptst_mask_select": (_i, [_f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, _f]),
+    "gptst_mask_ws_ints": (_i, []),
+    "gptst_mask_adaptive": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
+    "gptst_mask_random": (_i, [_f, _f, _f, _f, _l, _f]),
     "gptst_loss_parts": (_i, []),
     "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _f]),

@@ -279,6 +279,79 @@ def time_adaptive_proj(x, Wt, bt, prec=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# on-device mask construction (row f1)
+# ---------------------------------------------------------------------------------------------------
+def mask_labels(prob):
+    """prob (..., H) fp32 -> (label uint8 (n,), counts int32 (H,)): arg-max class of every cell and the class histogram."""
+    prob = prob.contiguous()
+    _chk(prob)
+    H = prob.shape[-1]
+    n = prob.numel() // H
+    label = torch.empty(n, dtype=torch.uint8, device=prob.device)
+    counts = torch.empty(H, dtype=torch.int32, device=prob.device)
+    _lib.check(_lib.lib().gptst_mask_labels(_p(prob), _p(label), _p(counts), n, H, _stream()), "gptst_mask_labels")
+    return label, counts
+
+
+def mask_select_adaptive(label, counts, plan, u1, u2, i0: int, all_type: bool):
+    """Phase-2 mask (GPTST.py:344-413) from the class labels, the host-made plan and the two uniform draws; (n, i0) int64."""
+    n, H = label.numel(), counts.numel()
+    if plan.dtype != torch.int64 or plan.numel() != H + 2 or u1.numel() != n or u2.numel() != n:
+        raise RuntimeError("mask_select_adaptive: inconsistent arguments")
+    final = torch.empty((n, i0), dtype=torch.int64, device=label.device)
+    m_ada = torch.empty(n, dtype=torch.uint8, device=label.device)
+    rc = _lib.lib().gptst_mask_select(_p(label), _p(counts), _p(plan), _p(u1.contiguous()), _p(u2.contiguous()), _p(m_ada), _p(final),
+                                      n, H, i0, int(all_type), 2, _stream())
+    _lib.check(rc, "gptst_mask_select")
+    return final
+
+
+def mask_select_random(u, k_dev):
+    """Phase-1 mask (GPTST.py:316-323): zero the k largest entries of u (ties in index order); k_dev is a 1-element int64
+    device tensor.  Returns (n,) int64."""
+    n = u.numel()
+    final = torch.empty((n, 1), dtype=torch.int64, device=u.device)
+    rc = _lib.lib().gptst_mask_select(None, None, _p(k_dev), _p(u.contiguous()), None, None, _p(final), n, 1, 1, 0, 1, _stream())
+    _lib.check(rc, "gptst_mask_select")
+    return final.view(-1)
+
+
+def mask_adaptive(prob, label_override, plan, u1, u2, i0: int, all_type: bool):
+    """Phase-2 mask through the multi-CTA pipeline: (n, i0) int64, 1 = keep.  prob (..., H); label_override (n,) int or None."""
+    prob = prob.contiguous()
+    _chk(prob)
+    H = prob.shape[-1]
+    n = prob.numel() // H
+    dev = prob.device
+    L = _lib.lib()
+    if plan.dtype != torch.int64 or plan.numel() != H + 2 or u1.numel() != n or u2.numel() != n:
+        raise RuntimeError("mask_adaptive: inconsistent arguments")
+    lab_in = None if label_override is None else label_override.reshape(-1).to(torch.uint8).contiguous()
+    label = torch.empty(n, dtype=torch.uint8, device=dev)
+    m_ada = torch.empty(n, dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.gptst_mask_ws_ints(), dtype=torch.int32, device=dev)
+    final = torch.empty((n, i0), dtype=torch.int64, device=dev)
+    st = _stream()
+    _count(7)   # label + 3 passes per selection + 2 (normally idle) slow-path launches
+    rc = L.gptst_mask_adaptive(_p(prob), _p(lab_in), _p(plan), _p(u1.contiguous()), _p(u2.contiguous()), _p(label), _p(m_ada), _p(ws),
+                               _p(final), n, H, i0, int(all_type), st)
+    _lib.check(rc, "gptst_mask_adaptive")
+    return final
+
+
+def mask_random(u, k_dev):
+    """Phase-1 mask through the multi-CTA pipeline: zero the k largest entries of u (ties in index order); (n,) int64."""
+    n = u.numel()
+    L = _lib.lib()
+    ws = torch.empty(L.gptst_mask_ws_ints(), dtype=torch.int32, device=u.device)
+    final = torch.empty(n, dtype=torch.int64, device=u.device)
+    st = _stream()
+    _count(3)
+    _lib.check(L.gptst_mask_random(_p(k_dev), _p(u.contiguous()), _p(ws), _p(final), n, st), "gptst_mask_random")
+    return final
+
+
+# ---------------------------------------------------------------------------------------------------
 # fused pre-training loss (row f2): value + analytic gradients in one pass
 # ---------------------------------------------------------------------------------------------------
 class _FusedLoss(torch.autograd.Function):

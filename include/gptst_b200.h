@@ -105,6 +105,27 @@ int gptst_linear_bwd_acc_splits(long rows, int D);
 int gptst_linear_bwd_acc(const float* dY, const float* X, const float* W, float* dX_io, float* dW_part, float* db_part,
                          long rows, int D, int prec, int splits, void* stream);
 
+/* ---- on-device mask construction (GPTST.py:312-413) ------------------------------------------
+ * mask_labels: label[i] = argmax_h prob[i][h] (uint8, first maximum), counts[h] = class histogram (int32, zeroed here).
+ * mask_select: mode 2 (adaptive phase): plan = {shuffled class order[0..H), adaptive_num, random_num} (int64), u1 / u2 the two
+ *              torch.rand draws of the reference, m_ada n bytes of scratch; classes are taken in `order` until the adaptive
+ *              budget is covered (all but the last masked outright when all_type != 0), the last one is sub-sampled by an exact
+ *              top-k of u1 (ties in index order, as the reference's stable sort), then random_num more cells by a top-k of u2.
+ *              mode 1 (random phase): plan[0] = number of cells to mask by a top-k of u1.
+ *              final_mask (n, i0) int64: 1 = keep, 0 = masked.  One CTA, no host synchronisation.                       */
+int gptst_mask_labels(const float* prob, unsigned char* label, int* counts, long n, int H, void* stream);
+int gptst_mask_select(const unsigned char* label, const int* counts, const long long* plan, const float* u1, const float* u2,
+                      unsigned char* m_ada, long long* final_mask, long n, int H, int i0, int all_type, int mode, void* stream);
+
+/* The same masks through a multi-CTA pipeline (histogram / collect / apply passes per selection; this is what the model
+ * launches -- the one-CTA kernel above is its exact slow path and specification).  ws: gptst_mask_ws_ints() int32 scratch;
+ * label, m_ada: n bytes scratch each; label_in != NULL supplies the class labels instead of arg-max(prob).                 */
+int gptst_mask_ws_ints(void);
+int gptst_mask_adaptive(const float* prob, const unsigned char* label_in, const long long* plan, const float* u1,
+                        const float* u2, unsigned char* label, unsigned char* m_ada, int* ws, long long* final_mask, long n,
+                        int H, int i0, int all_type, void* stream);
+int gptst_mask_random(const long long* k_dev, const float* u, int* ws, long long* final_mask, long n, void* stream);
+
 /* ---- fused pre-training loss + analytic gradients ------------------------------------
  * mode 0: probe loss mean|(o - x)*m| ; mode 1: masked MAE of Run.py:91-101 / lib/metrics.py:11-18 (inverse z-score with
  * mean/std, keep true*m > thr) ; plus kl_w * KLDivLoss(sum)(log prob, hs) (BasicTrainer.py:84-86) when kl_w != 0.

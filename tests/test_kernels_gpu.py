@@ -283,3 +283,75 @@ def test_fused_adam_clip_matches_torch():
         for a, b in zip(pa, pb):
             assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (it, (a - b).abs().max().item())
     assert int(opt.step_count.item()) == 6
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ada_type", ["all", "half"])
+@pytest.mark.parametrize("epoch", [11, 50, 200, 300])
+def test_mask_kernels_match_torch_restatement_and_oracle(ada_type, epoch):
+    """Row f1: the selection kernels give bit-identical masks to the sort-based torch restatement (same draws) and to the
+    oracle's restatement of the reference loop -- incl. coarse keys (many exact ties at the threshold, resolved in index
+    order like the reference's stable sort) and a dominant class."""
+    import random
+    from gptst_b200 import ops
+    from gptst_b200.GPTST import Hypergraph_encoder, _exact_count_mask
+    from util import make_cfg
+    for seed in range(5):
+        B, N, H = 4, 37, 10
+        enc = Hypergraph_encoder(make_cfg(N=N, D=64, ada_type=ada_type)).cuda()
+        n = B * 12 * N
+        probs = torch.rand(B, 12, N, H, generator=torch.Generator().manual_seed(seed)).cuda()
+        if seed == 4:
+            probs[..., 3] += 5
+        src = torch.zeros(B, 12, N, 3, device="cuda")
+        random.seed(seed)
+        torch.manual_seed(seed)
+        got = enc._adaptive_mask(src, probs, epoch)
+        random.seed(seed)
+        torch.manual_seed(seed)
+        want = enc._adaptive_mask_torch(src, probs, epoch)
+        assert torch.equal(got, want), (ada_type, epoch, seed)
+        assert int((1 - got).sum()) == int(n * 0.25)
+        # coarse keys: draws quantised to 1/64 -> hundreds of exact ties around every threshold; the reference semantics are
+        # those of torch.sort on CUDA (a stable radix sort: ties keep index order), replayed here with the same torch ops
+        label, counts = ops.mask_labels(probs)
+        assert torch.equal(label.long(), probs.argmax(-1).reshape(-1))
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        u1 = torch.floor(torch.rand(n, device="cuda", generator=g) * 64) / 64
+        u2 = torch.floor(torch.rand(n, device="cuda", generator=g) * 64) / 64
+        _, ada, rnd = O.mask_budgets(n, 0.25, 0.5, epoch, 10, 300)
+        order = list(range(H))
+        random.Random(seed).shuffle(order)
+        plan = torch.tensor(order + [ada, rnd], dtype=torch.int64, device="cuda")
+        flat = label.long()
+        cnt = torch.bincount(flat, minlength=H)
+        picked, total = 0, 0
+        while total < ada:
+            total += int(cnt[order[picked]])
+            picked += 1
+        chosen = order[:picked]
+        isin = lambda cls: (flat.unsqueeze(1) == torch.tensor(cls, device="cuda").view(1, -1)).any(1).long() if cls else torch.zeros_like(flat)
+        if ada_type == "all" and picked >= 2:
+            full, part = isin(chosen[:-1]), isin(chosen[-1:])
+        else:
+            full, part = torch.zeros_like(flat), isin(chosen)
+        m_ada = _exact_count_mask(part * u1, ada - int(full.sum())) * (1 - full)
+        ref = m_ada * _exact_count_mask(m_ada * u2, rnd)
+        for name, m in (("pipeline", ops.mask_adaptive(probs, None, plan, u1, u2, 1, ada_type == "all").view(-1)),
+                        ("one-CTA", ops.mask_select_adaptive(label, counts, plan, u1, u2, 1, ada_type == "all").view(-1))):
+            assert torch.equal(m, ref), ("ties", name, ada_type, epoch, seed)
+
+
+def test_mask_random_phase_kernel():
+    """Phase-1 mask: zero the k largest draws, ties in index order (GPTST.py:316-323)."""
+    from gptst_b200 import ops
+    from gptst_b200.GPTST import _exact_count_mask
+    for n, k, quant in ((130560, 32640, 0), (5000, 1250, 32), (4097, 4096, 0), (1000, 0, 0), (777, 777, 4)):
+        g = torch.Generator(device="cuda").manual_seed(n)
+        u = torch.rand(n, device="cuda", generator=g)
+        if quant:
+            u = torch.floor(u * quant) / quant
+        kd = torch.tensor([k], dtype=torch.int64, device="cuda")
+        want = _exact_count_mask(u, k)
+        assert torch.equal(ops.mask_select_random(u, kd), want), ("one-CTA", n, k, quant)
+        assert torch.equal(ops.mask_random(u, kd), want), ("pipeline", n, k, quant)
