@@ -98,8 +98,11 @@ class PretrainStep:
         torch.cuda.synchronize()
         from . import ops as _ops
         l0 = _ops.launch_count()
+        # capture on a HIGH-priority stream: the main chain's kernel nodes inherit it, while the table prologues and their
+        # gradients sit on default (lowest) priority side streams and only fill the SMs the main chain leaves idle
+        cap_stream = torch.cuda.Stream(device=dev, priority=-1)
         try:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=cap_stream):
                 static_loss = self._body(static_src, epoch)
         finally:
             self.enc.plan_override = None
