@@ -179,38 +179,46 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
         const int r0 = rbase + n0;
         unsigned char* Xw = Xs + (size_t)n0 * ROWB;
         unsigned char* Gw = Gs + (size_t)n0 * ROWB;
-        stage16(Xw, Xg, rs, r0, R, lane);
+        // dY first, X second (two cp.async groups): the dy conversion and the dX product only need dY, so the X rows
+        // keep streaming in underneath them; Y goes straight to registers so its latency overlaps the staging as well
         stage16(Gw, dYg, rs, r0, R, lane);
-        cp_async_wait_all();
-        __syncwarp();
-        // ---- pass 1: max |X|, max |dY| of the chunk -> one power-of-two scale each
-        {
-            float mx = 0.f, mg = 0.f;
+        cp_async_commit();
+        stage16(Xw, Xg, rs, r0, R, lane);
+        cp_async_commit();
+        constexpr bool PREY = NW * 32 * MINB <= 512;   // room for 32 more live registers (cap >= 128 per thread)
+        float4 yv[PREY ? 8 : 1];
+        if (PREY && act) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
-                const float4 a = *reinterpret_cast<const float4*>(Xw + (size_t)r * ROWB + ch * 16);
+                yv[k] = (r0 + r < R) ? *reinterpret_cast<const float4*>(Yg + (long)(r0 + r) * rs + ch * 4)
+                                     : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+        }
+        cp_async_wait_group<1>();
+        __syncwarp();
+        // ---- max |dY| of the chunk -> one power-of-two scale
+        {
+            float mg = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
                 const float4 b = *reinterpret_cast<const float4*>(Gw + (size_t)r * ROWB + ch * 16);
-                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
                 mg = fmaxf(mg, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
-            }
-            if (lane == 0) { cmax[warp] = mx; cmax[NW + warp] = mg; }
+            for (int o = 16; o > 0; o >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+            if (lane == 0) cmax[NW + warp] = mg;
         }
         __syncthreads();
-        float2 sx, sg;
+        float2 sg;
         {
-            float mx = 0.f, mg = 0.f;
+            float mg = 0.f;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { mx = fmaxf(mx, cmax[w]); mg = fmaxf(mg, cmax[NW + w]); }
-            sx = pow2_scale_for_fp16(mx);
+            for (int w = 0; w < NW; ++w) mg = fmaxf(mg, cmax[NW + w]);
             sg = pow2_scale_for_fp16(mg);
         }
-        // ---- pass 2: dy = dY * act'(Y) -> dRes, column sums, planes ; X -> planes
+        // ---- dy = dY * act'(Y) -> dRes, column sums, planes
         {
             float4 f[8];
 #pragma unroll
@@ -219,7 +227,7 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
                 f[k] = *reinterpret_cast<const float4*>(Gw + (size_t)r * ROWB + ch * 16);
                 if (r0 + r < R) {
                     if (act) {
-                        const float4 y = *reinterpret_cast<const float4*>(Yg + (long)(r0 + r) * rs + ch * 4);
+                        const float4 y = PREY ? yv[PREY ? k : 0] : *reinterpret_cast<const float4*>(Yg + (long)(r0 + r) * rs + ch * 4);
                         f[k].x = lrelu_grad(y.x, f[k].x); f[k].y = lrelu_grad(y.y, f[k].y);
                         f[k].z = lrelu_grad(y.z, f[k].z); f[k].w = lrelu_grad(y.w, f[k].w);
                     }
@@ -235,22 +243,6 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
                 split_h2<PREC>(f[k].x * sg.x, f[k].y * sg.x, h0, l0);
                 split_h2<PREC>(f[k].z * sg.x, f[k].w * sg.x, h1, l1);
                 unsigned char* row = Gw + (size_t)r * ROWB + ch * 8;
-                *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
-                f[k] = *reinterpret_cast<const float4*>(Xw + (size_t)r * ROWB + ch * 16);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
-                uint32_t h0, l0, h1, l1;
-                split_h2<PREC>(f[k].x * sx.x, f[k].y * sx.x, h0, l0);
-                split_h2<PREC>(f[k].z * sx.x, f[k].w * sx.x, h1, l1);
-                unsigned char* row = Xw + (size_t)r * ROWB + ch * 8;
                 *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
                 *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
             }
@@ -296,6 +288,46 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
                         }
                     }
                 }
+            }
+        }
+        // ---- X landed meanwhile: max |X| -> scale -> planes
+        cp_async_wait_group<0>();
+        __syncwarp();
+        {
+            float mx = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+                const float4 a = *reinterpret_cast<const float4*>(Xw + (size_t)r * ROWB + ch * 16);
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) cmax[warp] = mx;
+        }
+        __syncthreads();
+        float2 sx;
+        {
+            float mx = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) mx = fmaxf(mx, cmax[w]);
+            sx = pow2_scale_for_fp16(mx);
+            float4 f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+                f[k] = *reinterpret_cast<const float4*>(Xw + (size_t)r * ROWB + ch * 16);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+                uint32_t h0, l0, h1, l1;
+                split_h2<PREC>(f[k].x * sx.x, f[k].y * sx.x, h0, l0);
+                split_h2<PREC>(f[k].z * sx.x, f[k].w * sx.x, h1, l1);
+                unsigned char* row = Xw + (size_t)r * ROWB + ch * 8;
+                *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
             }
         }
         __syncthreads();   // every warp's planes are in place
