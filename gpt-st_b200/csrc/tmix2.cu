@@ -3,10 +3,11 @@
 //     dM[n][t][s]  = sum_{b,j} dy[b,t,n,j] x[b,s,n,j]        (gradient of the mix matrix)
 // One warp per (node, batch range); per (b, n) the warp owns a 12 x 64 tile of dy and of x.  Both products run on the
 // tensor cores (mma.sync m16n8k16, fp16-split operands, see mma_f16.cuh) with T = 12 padded to 16:
-//     dM tile   : M-dim = t, N-dim = s, K = 64 columns  -> A and B fragments are float2 loads straight from global
-//                 memory (rows g / g+8, columns 2t..2t+1), no shared memory at all;
+//     dM tile   : M-dim = t, N-dim = s, K = 64 columns  -> A and B fragments by ldmatrix from the fp32 tiles the warp staged
+//                 in shared memory (same k permutation on both operands, see mma_f16.cuh);
 //     mix tile  : M-dim = s, N-dim = 8 columns, K = t   -> A = M_n^T (8 registers per node, loaded once per warp),
-//                 B = dy[t = 2t', 2t'+1][column g]: a second, transposed-friendly read of the same tile (L1 hit).
+//                 B = dy[t = 2t', 2t'+1][column g] read from the same shared-memory tile; the update goes back through
+//                 shared memory so that global memory only ever sees 16-byte chunks of full rows.
 // dy is a gradient: each tile gets one power-of-two scale from its max |.| (exact, undone in fp32).  dM accumulates in
 // fp32 registers over the warp's batches; partials per batch split are summed by the caller (deterministic).
 // Replaces tmix(transpose, accumulate) + tmix_dM (24 + 50 us at B=64, N=170) with one pass over dy, x and dx.
@@ -19,18 +20,41 @@ namespace tm2 {
 using namespace hf;
 constexpr int T = 12, D = 64;
 
+// Shared-memory layout per warp: two 16-row tiles (dy, x) of 272-byte slots; rows 12..15 stay zero.  Rows are staged with
+// 16-byte cp.async chunks (two full 256-byte rows per warp request: 4 cache lines per request instead of the 8 that a
+// fragment-shaped global access touches -- the L1 tag stage, not DRAM, limited the first version of this kernel).
+constexpr int TROWS = 16;
+constexpr int WARP_BYTES = 2 * TROWS * ROWB;
+
+__device__ __forceinline__ void stage_tile(unsigned char* tile, const float* base, size_t slab, int lane) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {                  // 12 rows x 16 chunks = 192 chunks
+        const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+        cp_async16(tile + (size_t)r * ROWB + ch * 16, base + (size_t)r * slab + ch * 4);
+    }
+}
+
 template <int PREC>
 __global__ void __launch_bounds__(256, 3)
 tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ M,
                 float* __restrict__ dx_io, float* __restrict__ dM_part, int B, int N, int bps) {
+    extern __shared__ __align__(128) unsigned char smraw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    unsigned char* Ty = smraw + (size_t)warp * WARP_BYTES;      // dy tile (fp32 rows)
+    unsigned char* Tx = Ty + TROWS * ROWB;                      // x tile, later the staging area of the dx update
+    // zero the padding rows 12..15 of both tiles once
+    for (int i = lane; i < 2 * 4 * (ROWB / 16); i += 32) {
+        const int tile = i / (4 * (ROWB / 16)), rem = i % (4 * (ROWB / 16));
+        *reinterpret_cast<float4*>((tile ? Tx : Ty) + (size_t)(T + rem / (ROWB / 16)) * ROWB + (rem % (ROWB / 16)) * 16) =
+            make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int n = blockIdx.x * 8 + warp;
     if (n >= N) return;
     const int b0 = blockIdx.y * bps;
     const int b1 = (b0 + bps < B) ? b0 + bps : B;
     const size_t slab = (size_t)N * D;
-    const bool r1ok = g + 8 < T;                 // second fragment row (t or s = g + 8) exists
+    const bool r1ok = g + 8 < T;
 
     // ---- A fragments of the mix: A[m = s][k = tt] = M[n][tt][s], one power-of-two scale per node
     uint32_t mh[4], ml[4];
@@ -40,7 +64,6 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
         float a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            // i: 0,1 -> (s = g, tt = 2t, 2t+1)  2,3 -> (s = g+8, ..)  4,5 -> (s = g, tt = 2t+8, 2t+9)  6,7 -> (s = g+8, ..)
             const int tt = 2 * t + (i & 1) + ((i & 4) ? 8 : 0);
             const int s = g + ((i & 2) ? 8 : 0);
             a[i] = (tt < T && s < T) ? Mn[tt * T + s] : 0.f;
@@ -58,7 +81,7 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
         split_h2<PREC>(a[6] * sc.x, a[7] * sc.x, mh[3], ml[3]);
     }
 
-    float dm[2][4];                               // dM tile: [s tile][C fragment]
+    float dm[2][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) dm[0][i] = dm[1][i] = 0.f;
 
@@ -66,43 +89,52 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
         const float* dyp = dy + (size_t)b * T * slab + (size_t)n * D;
         const float* xp = x + (size_t)b * T * slab + (size_t)n * D;
         float* dxp = dx_io + (size_t)b * T * slab + (size_t)n * D;
-        // ---- dy tile in the A layout of the dM product: rows g, g+8; columns 16k + 2t (+8)
-        float2 ya[4][4];
+        __syncwarp();                               // the previous iteration's readers of Ty / Tx are done
+        stage_tile(Ty, dyp, slab, lane);
+        stage_tile(Tx, xp, slab, lane);
+        cp_async_commit();
+        // the dx tile this warp will update: same chunk mapping, straight to registers (overlaps the staging)
+        float4 dxv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+            dxv[k] = *reinterpret_cast<const float4*>(dxp + (size_t)r * slab + ch * 4);
+        }
+        cp_async_wait_group<0>();
+        __syncwarp();
+        // ---- tile max of dy -> power-of-two scale
         float mx = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = 16 * k + 2 * t;
-            ya[k][0] = *reinterpret_cast<const float2*>(dyp + (size_t)g * slab + c);
-            ya[k][2] = *reinterpret_cast<const float2*>(dyp + (size_t)g * slab + c + 8);
-            ya[k][1] = r1ok ? *reinterpret_cast<const float2*>(dyp + (size_t)(g + 8) * slab + c) : make_float2(0.f, 0.f);
-            ya[k][3] = r1ok ? *reinterpret_cast<const float2*>(dyp + (size_t)(g + 8) * slab + c + 8) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fabsf(ya[k][i].x), fabsf(ya[k][i].y)));
+        for (int k = 0; k < 6; ++k) {
+            const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+            const float4 v = *reinterpret_cast<const float4*>(Ty + (size_t)r * ROWB + ch * 16);
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         const float2 sc = pow2_scale_for_fp16(mx);
-        // ---- dM tile += dy x^T
+        // ---- dM tile += dy x^T   (both operands by ldmatrix from the fp32 tiles: same k permutation on both sides)
         {
             float th[2][4], tl[2][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) th[0][i] = th[1][i] = tl[0][i] = tl[1][i] = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int c = 16 * k + 2 * t;
-                uint32_t ah[4], al[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_h2<PREC>(ya[k][i].x * sc.x, ya[k][i].y * sc.x, ah[i], al[i]);
-                // B fragments: x rows s = g (tile 0) and s = g + 8 (tile 1), same columns
-                const float2 x00 = *reinterpret_cast<const float2*>(xp + (size_t)g * slab + c);
-                const float2 x01 = *reinterpret_cast<const float2*>(xp + (size_t)g * slab + c + 8);
-                const float2 x10 = r1ok ? *reinterpret_cast<const float2*>(xp + (size_t)(g + 8) * slab + c) : make_float2(0.f, 0.f);
-                const float2 x11 = r1ok ? *reinterpret_cast<const float2*>(xp + (size_t)(g + 8) * slab + c + 8) : make_float2(0.f, 0.f);
-                uint32_t bh[4], bl[4];
-                split_h2<PREC>(x00.x, x00.y, bh[0], bl[0]);
-                split_h2<PREC>(x01.x, x01.y, bh[1], bl[1]);
-                split_h2<PREC>(x10.x, x10.y, bh[2], bl[2]);
-                split_h2<PREC>(x11.x, x11.y, bh[3], bl[3]);
+                uint32_t f[4], ah[4], al[4], bh[4], bl[4];
+                const uint32_t aaddr = smem_u32(Ty + (size_t)(lane & 7) * ROWB + (16 * k + 4 * (lane >> 3)) * 4);
+                const uint32_t baddr = smem_u32(Tx + (size_t)(lane & 7) * ROWB + (16 * k + 4 * (lane >> 3)) * 4);
+                ldsm_x4(f, aaddr);
+                split_h2<PREC>(__uint_as_float(f[0]) * sc.x, __uint_as_float(f[1]) * sc.x, ah[0], al[0]);
+                split_h2<PREC>(__uint_as_float(f[2]) * sc.x, __uint_as_float(f[3]) * sc.x, ah[2], al[2]);
+                ldsm_x4(f, aaddr + 8 * ROWB);
+                split_h2<PREC>(__uint_as_float(f[0]) * sc.x, __uint_as_float(f[1]) * sc.x, ah[1], al[1]);
+                split_h2<PREC>(__uint_as_float(f[2]) * sc.x, __uint_as_float(f[3]) * sc.x, ah[3], al[3]);
+                ldsm_x4(f, baddr);                  // x rows s = 0..7  -> B fragments of tile 0
+                split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), bh[0], bl[0]);
+                split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), bh[1], bl[1]);
+                ldsm_x4(f, baddr + 8 * ROWB);       // x rows s = 8..15 -> tile 1
+                split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), bh[2], bl[2]);
+                split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), bh[3], bl[3]);
                 if (PREC == PREC_3XTF32) {
                     mma_f16(tl[0], al, bh[0], bh[1]);
                     mma_f16(tl[1], al, bh[2], bh[3]);
@@ -118,29 +150,32 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
                 dm[1][i] = fmaf(th[1][i] + tl[1][i], sc.y, dm[1][i]);
             }
         }
-        // ---- dx tile += M^T dy : B[k = tt][n = column] = dy[tt][8j + g]
+        __syncwarp();                               // x tile consumed: its slots become the staging area of the update
+        // ---- update tile = M^T dy : B[k = tt][n = column] = dy[tt][8j + g]  (conflict-free scalar reads of the fp32 tile)
         const float un = sc.y * m_inv;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = 8 * j + g;
-            const float v0 = dyp[(size_t)(2 * t) * slab + c], v1 = dyp[(size_t)(2 * t + 1) * slab + c];
-            float v2 = 0.f, v3 = 0.f;
-            if (2 * t + 8 < T) { v2 = dyp[(size_t)(2 * t + 8) * slab + c]; v3 = dyp[(size_t)(2 * t + 9) * slab + c]; }
+            const float v0 = *reinterpret_cast<const float*>(Ty + (size_t)(2 * t) * ROWB + c * 4);
+            const float v1 = *reinterpret_cast<const float*>(Ty + (size_t)(2 * t + 1) * ROWB + c * 4);
+            const float v2 = *reinterpret_cast<const float*>(Ty + (size_t)(2 * t + 8) * ROWB + c * 4);   // rows >= 12 are zero
+            const float v3 = *reinterpret_cast<const float*>(Ty + (size_t)(2 * t + 9) * ROWB + c * 4);
             uint32_t bh0, bl0, bh1, bl1;
             split_h2<PREC>(v0 * sc.x, v1 * sc.x, bh0, bl0);
             split_h2<PREC>(v2 * sc.x, v3 * sc.x, bh1, bl1);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             mma3<PREC>(acc, mh, ml, bh0, bh1, bl0, bl1);
-            float2* p0 = reinterpret_cast<float2*>(dxp + (size_t)g * slab + 8 * j + 2 * t);
-            float2 o = *p0;
-            o.x = fmaf(acc[0], un, o.x); o.y = fmaf(acc[1], un, o.y);
-            *p0 = o;
-            if (r1ok) {
-                float2* p1 = reinterpret_cast<float2*>(dxp + (size_t)(g + 8) * slab + 8 * j + 2 * t);
-                float2 o1 = *p1;
-                o1.x = fmaf(acc[2], un, o1.x); o1.y = fmaf(acc[3], un, o1.y);
-                *p1 = o1;
-            }
+            *reinterpret_cast<float2*>(Tx + (size_t)g * ROWB + (8 * j + 2 * t) * 4) = make_float2(acc[0] * un, acc[1] * un);
+            if (r1ok) *reinterpret_cast<float2*>(Tx + (size_t)(g + 8) * ROWB + (8 * j + 2 * t) * 4) = make_float2(acc[2] * un, acc[3] * un);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+            const float4 u = *reinterpret_cast<const float4*>(Tx + (size_t)r * ROWB + ch * 16);
+            float4 o = dxv[k];
+            o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+            *reinterpret_cast<float4*>(dxp + (size_t)r * slab + ch * 4) = o;
         }
     }
     // ---- dM partial of this batch range: C fragment (t = g / g+8 ; s = 8*tile + 2t, 2t+1)
@@ -180,7 +215,16 @@ extern "C" int gptst_tmix_bwd(const float* dy, const float* x, const float* M, f
     const int bps = (B + splits - 1) / splits;
     dim3 grid((N + 7) / 8, splits);
     cudaStream_t st = (cudaStream_t)stream;
-    if (prec == 3) tm2::tmix_bwd_kernel<PREC_3XTF32><<<grid, 256, 0, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
-    else tm2::tmix_bwd_kernel<PREC_TF32><<<grid, 256, 0, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
+    const size_t smem = (size_t)8 * tm2::WARP_BYTES;
+    cudaError_t e;
+    if (prec == 3) {
+        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        tm2::tmix_bwd_kernel<PREC_3XTF32><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
+    } else {
+        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        tm2::tmix_bwd_kernel<PREC_TF32><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
+    }
     return (int)cudaGetLastError();
 }
