@@ -43,7 +43,7 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
         if (r < N) cp_async16(dst, xs + (size_t)r * D + ch * 4);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    stage_w_perm<PREC>(Wt, Wp, WSCALE, tid, NT);
+    stage_w_perm<PREC, NT>(Wt, Wp, WSCALE, tid);
     for (int i = tid; i < D; i += NT) bps[i] = bp[i];
     // ds: each thread keeps (at most two) float2 of the H x 64 block, the slab max goes through wmax
     constexpr int DSP = (16 * 32 + NT - 1) / NT;      // float2 items per thread (rows padded to 16)

@@ -84,7 +84,7 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
         if (r < N) cp_async16(dst, xs + (size_t)r * D + ch * 4);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    stage_w_perm<PREC>(Wt, Wp, WSCALE, tid, NT);
+    stage_w_perm<PREC, NT>(Wt, Wp, WSCALE, tid);
     for (int i = tid; i < D; i += NT) bps[i] = bp[i];
     for (int i = tid; i < 16 * ROWB / 16; i += NT) reinterpret_cast<float4*>(vpl)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 

@@ -65,15 +65,27 @@ gproj2_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
     stage16(Xs + (size_t)n0 * ROWB, Xg, rs, r0, R, lane);
     if (Res) stage16(Rs + (size_t)n0 * ROWB, Res + (long)grp * gs, rs, r0, R, lane);
     const float* Wg = W + (size_t)grp * D * D;
-    for (int i = tid; i < D * 16; i += NT) {
-        const int k = i >> 4, q4 = i & 15;
-        const float4 w = *reinterpret_cast<const float4*>(Wg + (size_t)k * D + q4 * 4);
-        uint32_t h0, l0, h1, l1;
-        split_h2<PREC>(w.x * WSCALE, w.y * WSCALE, h0, l0);
-        split_h2<PREC>(w.z * WSCALE, w.w * WSCALE, h1, l1);
-        unsigned char* row = Wt + (size_t)(16 * (k >> 4) + kperm(k & 15)) * ROWB + q4 * 8;
-        *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
+    {   // all of this thread's W_g loads are issued before the first one is consumed (a rolled loop serialises the latencies)
+        constexpr int WI = (D * 16 + NT - 1) / NT;
+        float4 wv[WI];
+#pragma unroll
+        for (int u = 0; u < WI; ++u) {
+            const int i = tid + u * NT;
+            wv[u] = (i < D * 16) ? *reinterpret_cast<const float4*>(Wg + (size_t)(i >> 4) * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < WI; ++u) {
+            const int i = tid + u * NT;
+            if (i < D * 16) {
+                const int k = i >> 4, q4 = i & 15;
+                uint32_t h0, l0, h1, l1;
+                split_h2<PREC>(wv[u].x * WSCALE, wv[u].y * WSCALE, h0, l0);
+                split_h2<PREC>(wv[u].z * WSCALE, wv[u].w * WSCALE, h1, l1);
+                unsigned char* row = Wt + (size_t)(16 * (k >> 4) + kperm(k & 15)) * ROWB + q4 * 8;
+                *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
+            }
+        }
     }
     for (int i = tid; i < D; i += NT) bs[i] = bias ? bias[(size_t)grp * D + i] : 0.f;
     cp_async_wait_all();
@@ -154,18 +166,31 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
     float* dRg = dRes ? dRes + (long)grp * gs : nullptr;
 
     const float* Wg = W + (size_t)grp * D * D;
-    for (int i = tid; i < D * 16; i += NT) {
-        const int k = i >> 4, q4 = i & 15;        // k = in index, columns out = 4*q4 .. 4*q4+3
-        float4 w;
-        if (flags & 2) w = make_float4(Wg[(size_t)(4 * q4) * D + k], Wg[(size_t)(4 * q4 + 1) * D + k], Wg[(size_t)(4 * q4 + 2) * D + k],
-                                       Wg[(size_t)(4 * q4 + 3) * D + k]);
-        else w = *reinterpret_cast<const float4*>(Wg + (size_t)k * D + q4 * 4);
-        uint32_t h0, l0, h1, l1;
-        split_h2<PREC>(w.x * WSCALE, w.y * WSCALE, h0, l0);
-        split_h2<PREC>(w.z * WSCALE, w.w * WSCALE, h1, l1);
-        unsigned char* row = Wt + (size_t)k * ROWB + q4 * 8;
-        *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
+    {   // issue all W_g loads of this thread first, convert afterwards
+        constexpr int WI = (D * 16 + NT - 1) / NT;
+        float4 wv[WI];
+#pragma unroll
+        for (int u = 0; u < WI; ++u) {
+            const int i = tid + u * NT;
+            const int k = i >> 4, q4 = i & 15;        // k = in index, columns out = 4*q4 .. 4*q4+3
+            if (i >= D * 16) wv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (flags & 2) wv[u] = make_float4(Wg[(size_t)(4 * q4) * D + k], Wg[(size_t)(4 * q4 + 1) * D + k],
+                                                    Wg[(size_t)(4 * q4 + 2) * D + k], Wg[(size_t)(4 * q4 + 3) * D + k]);
+            else wv[u] = *reinterpret_cast<const float4*>(Wg + (size_t)k * D + q4 * 4);
+        }
+#pragma unroll
+        for (int u = 0; u < WI; ++u) {
+            const int i = tid + u * NT;
+            if (i < D * 16) {
+                const int k = i >> 4, q4 = i & 15;
+                uint32_t h0, l0, h1, l1;
+                split_h2<PREC>(wv[u].x * WSCALE, wv[u].y * WSCALE, h0, l0);
+                split_h2<PREC>(wv[u].z * WSCALE, wv[u].w * WSCALE, h1, l1);
+                unsigned char* row = Wt + (size_t)k * ROWB + q4 * 8;
+                *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
+            }
+        }
     }
 
     float dwm[TPW][4];

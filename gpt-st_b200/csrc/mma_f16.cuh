@@ -158,21 +158,31 @@ __device__ __forceinline__ float2 pow2_scale_for_fp16(float m) {
 //     logical {2t, 2t+1, 2t+8, 2t+9}  <->  physical {t, 4+t, 8+t, 12+t},
 // and the weight is staged with the same permutation, so the contraction is unchanged.
 // stage_w_perm: W (64 x 64 fp32, [out][in] as nn.Linear stores it) * scale -> Wt rows = out, hi|lo planes along permuted in.
-template <int PREC>
-__device__ __forceinline__ void stage_w_perm(unsigned char* Wt, const float* __restrict__ W, float scale, int tid, int nthreads) {
-    for (int i = tid; i < 64 * 16; i += nthreads) {
-        const int o = i >> 4, q4 = i & 15;
-        const float4 w = *reinterpret_cast<const float4*>(W + (size_t)o * 64 + q4 * 4);
-        const int q = q4 & 3;
-        const int base = 16 * (q4 >> 2) + ((q >= 2) ? 8 : 0) + (q & 1);
-        const float wv[4] = {w.x * scale, w.y * scale, w.z * scale, w.w * scale};
-        __half* hrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB);
-        __half* lrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB + LO);
+template <int PREC, int NT>
+__device__ __forceinline__ void stage_w_perm(unsigned char* Wt, const float* __restrict__ W, float scale, int tid) {
+    constexpr int WI = (64 * 16 + NT - 1) / NT;
+    float4 wv[WI];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const __half h = __float2half_rn(wv[e]);
-            hrow[base + 2 * e] = h;
-            lrow[base + 2 * e] = (PREC == PREC_3XTF32) ? __float2half_rn(wv[e] - __half2float(h)) : __float2half_rn(0.f);
+    for (int u = 0; u < WI; ++u) {               // all loads first: a rolled loop would serialise the global latencies
+        const int i = tid + u * NT;
+        wv[u] = (i < 64 * 16) ? *reinterpret_cast<const float4*>(W + (size_t)(i >> 4) * 64 + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < WI; ++u) {
+        const int i = tid + u * NT;
+        if (i < 64 * 16) {
+            const int o = i >> 4, q4 = i & 15;
+            const int q = q4 & 3;
+            const int base = 16 * (q4 >> 2) + ((q >= 2) ? 8 : 0) + (q & 1);
+            const float wq[4] = {wv[u].x * scale, wv[u].y * scale, wv[u].z * scale, wv[u].w * scale};
+            __half* hrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB);
+            __half* lrow = reinterpret_cast<__half*>(Wt + (size_t)o * ROWB + LO);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __half h = __float2half_rn(wq[e]);
+                hrow[base + 2 * e] = h;
+                lrow[base + 2 * e] = (PREC == PREC_3XTF32) ? __float2half_rn(wq[e] - __half2float(h)) : __float2half_rn(0.f);
+            }
         }
     }
 }
