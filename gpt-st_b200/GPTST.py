@@ -30,6 +30,13 @@ import torch.nn.functional as F
 from . import ops
 
 
+def _affine(lin, x):
+    """nn.Linear with one input feature as a single broadcast multiply-add (a K = 1 GEMM plus a bias kernel otherwise)."""
+    if lin.in_features == 1:
+        return torch.addcmul(lin.bias, x, lin.weight.view(-1))
+    return lin(x)
+
+
 def _uninit(*shape):
     # the reference registers uninitialised torch.FloatTensor pools (ref :13-17,92-93,149-150); Run.py:79-85 fills them
     return nn.Parameter(torch.empty(*shape))
@@ -48,14 +55,26 @@ class MLP_RL(nn.Module):
         self.bias_pool_tem = _uninit(embed_dim, hidden_dim)
         self.device = device
 
-    def forward(self, eb, time_eb, node_eb):
-        h0 = self.ln1(eb)                                                         # (B,T,N,D)
-        Wn = torch.einsum("nd,dio->nio", node_eb, self.weights_pool_spa)
-        bn = node_eb @ self.bias_pool_spa
-        h1 = ops.node_adaptive_proj(h0, Wn, bn)
-        Wt = torch.einsum("btd,dio->btio", time_eb, self.weights_pool_tem)
-        bt = time_eb @ self.bias_pool_tem
-        h2 = ops.time_adaptive_proj(h1, Wt, bt)
+    def tables_spa(self, node_eb):
+        return torch.einsum("nd,dio->nio", node_eb, self.weights_pool_spa), node_eb @ self.bias_pool_spa
+
+    def tables_tem(self, time_eb):
+        return torch.einsum("btd,dio->btio", time_eb, self.weights_pool_tem), time_eb @ self.bias_pool_tem
+
+    def forward(self, eb, time_eb, node_eb, tables=None):
+        """tables = ((Wn, bn, event), (Wt, bt, event)) when the caller produced them on side streams."""
+        h0 = _affine(self.ln1, eb)                                                # (B,T,N,D)
+        if tables is None:
+            Wn, bn = self.tables_spa(node_eb)
+            h1 = ops.node_adaptive_proj(h0, Wn, bn)
+            Wt, bt = self.tables_tem(time_eb)
+            h2 = ops.time_adaptive_proj(h1, Wt, bt)
+        else:
+            (Wn, bn, ev_n), (Wt, bt, ev_t) = tables
+            torch.cuda.current_stream().wait_event(ev_n)
+            h1 = ops.node_adaptive_proj(h0, Wn, bn)
+            torch.cuda.current_stream().wait_event(ev_t)
+            h2 = ops.time_adaptive_proj(h1, Wt, bt)
         return self.ln3(h2)
 
 
@@ -268,10 +287,33 @@ class Hypergraph_encoder(nn.Module):
         self._k_cache = {}
 
     # -- mask scorer (both phases), ref :326-332 / :338-343
-    def _scores(self, source):
+    def _scores(self, source, aux=None):
+        """Mask scorer.  aux = two side streams: the time embedding + time-adaptive tables and the node-adaptive tables are
+        independent of the flow, so they run beside the first layer instead of in front of it (this chain sits on the
+        critical path of the adaptive phase: the encoder cannot start before the mask exists)."""
         i0 = self.input_base_dim
-        time_eb = self.teb4mask(source[:, :, 0, i0:i0 + 2])
-        logits = self.MLP_RL(source[..., 0:i0], time_eb, self.neb4mask)
+        if aux is None:
+            time_eb = self.teb4mask(source[:, :, 0, i0:i0 + 2])
+            logits = self.MLP_RL(source[..., 0:i0], time_eb, self.neb4mask)
+            return F.softmax(logits, dim=-1)
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        sa, sb = aux
+        sa.wait_event(fork)
+        with torch.cuda.stream(sa):
+            time_eb = self.teb4mask(source[:, :, 0, i0:i0 + 2])
+            Wt, bt = self.MLP_RL.tables_tem(time_eb)
+            ev_t = torch.cuda.Event()
+            ev_t.record(sa)
+        sb.wait_event(fork)
+        with torch.cuda.stream(sb):
+            Wn, bn = self.MLP_RL.tables_spa(self.neb4mask)
+            ev_n = torch.cuda.Event()
+            ev_n.record(sb)
+        for t_ in (Wt, bt, Wn, bn):
+            t_.record_stream(cur)
+        logits = self.MLP_RL(source[..., 0:i0], None, None, ((Wn, bn, ev_n), (Wt, bt, ev_t)))
         return F.softmax(logits, dim=-1)
 
     def _budgets(self, n_cells, epoch):
@@ -361,7 +403,7 @@ class Hypergraph_encoder(nn.Module):
         i0 = self.input_base_dim
         flow = source[..., 0:i0]
         if self.mode != "pretrain":
-            enc, _, _ = self.STHCN_encode(source, self.dim_in_flow(flow), pro)
+            enc, _, _ = self.STHCN_encode(source, _affine(self.dim_in_flow, flow), pro)
             return enc
         score = pro.get("score") if pro is not None else None     # (prob, event) computed on a side stream
         if epoch <= self.change_epoch:
@@ -387,7 +429,7 @@ class Hypergraph_encoder(nn.Module):
             final_mask = self._adaptive_mask(source, prob, epoch)
         final_mask = final_mask.detach()
         masked = torch.where(final_mask == 0, torch.full_like(flow, float(self.scaler_zeros)), final_mask * flow)
-        x_in = self.dim_in_flow(masked)
+        x_in = _affine(self.dim_in_flow, masked)
         enc, HS1, _ = self.STHCN_encode(source, x_in, pro)
         return enc, final_mask[..., :i0], prob, HS1.squeeze(-1).transpose(-1, -2)
 
@@ -444,7 +486,7 @@ class GPTST_Model(nn.Module):
         key = (dev.index, main.cuda_stream)
         if self._streams is None or self._streams[0] != key:
             self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(9)], [torch.cuda.Stream(device=dev) for _ in range(9)],
-                             torch.cuda.Stream(device=dev))
+                             torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev) for _ in range(2)])
         fork = torch.cuda.Event()
         fork.record(main)
         out = []
@@ -453,7 +495,7 @@ class GPTST_Model(nn.Module):
         s3 = self._streams[3]
         s3.wait_event(fork)
         with torch.cuda.stream(s3):
-            prob = self.encoder._scores(source)
+            prob = self.encoder._scores(source, self._streams[4])
             ev3 = torch.cuda.Event()
             ev3.record(s3)
         prob.record_stream(main)
