@@ -43,6 +43,12 @@ SIGNATURES = {
     "gptst_mask_ws_ints": (_i, []),
     "gptst_mask_adaptive": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
     "gptst_mask_random": (_i, [_f, _f, _f, _f, _l, _f]),
+    "gptst_time_mlp_chunks": (_i, [_i]),
+    "gptst_time_mlp_grad_floats": (_i, [_i, _i]),
+    "gptst_time_mlp_fwd": (_i, [_f] * 16 + [_i, _i, _i, _l, _f]),
+    "gptst_time_mlp_bwd": (_i, [_f] * 10 + [_i, _i, _i, _l, _f]),
+    "gptst_affine1_bwd_parts": (_i, [_l]),
+    "gptst_affine1_bwd": (_i, [_f, _f, _f, _l, _i, _i, _f]),
     "gptst_loss_parts": (_i, []),
     "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _f]),

@@ -1,0 +1,214 @@
+// Small parameter-side pieces of the pre-training step that sat on the critical tail of the captured graph as chains of
+// tiny library kernels (reference GPTST.py:187-219 time_feature / time_feature_spg, and the one-feature input embeddings
+// dim_in_flow / MLP_RL.ln1, GPTST.py:22, :298).
+//
+//   time_mlp_fwd / _bwd : the 5-linear time-embedding MLP   h0 = a Wd^T + bd + b Ww^T + bw ;  z1 = h0 W1^T + b1 ;
+//                         z2 = relu(z1) W2^T + b2 ;  out = relu(z2) W3^T + b3      on R rows (R = B*T or B), F inputs per
+//                         branch (1 or 12), e hidden units (16 or 4).  Forward: one launch (was ~12); backward: one launch
+//                         that writes per-row-chunk partials of every parameter gradient (was ~25 launches).
+//   affine1_bwd         : y = x w + b with one input feature: dw = sum_i dy[i,:] x[i], db = sum_i dy[i,:] in one pass over
+//                         dy (row-range partials, summed by the caller).
+// Everything is deterministic (fixed partial order, no floating-point atomics).
+#include "common.cuh"
+
+namespace gptst {
+namespace sm {
+
+constexpr int kE = 16;       // max hidden width
+constexpr int kF = 12;       // max inputs per branch
+constexpr int kRows = 32;    // rows per CTA
+
+struct MlpParams {
+    const float *Wd, *bd, *Ww, *bw, *W1, *b1, *W2, *b2, *W3, *b3;
+};
+
+// grid = ceil(R / kRows), block = kRows * kE threads: thread = (row, unit)
+__global__ void __launch_bounds__(kRows* kE) time_mlp_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, MlpParams p,
+                                                                float* __restrict__ h0, float* __restrict__ z1,
+                                                                float* __restrict__ z2, float* __restrict__ out, int R, int F,
+                                                                int e, long in_stride) {
+    __shared__ float W[3][kE * kE], Wi[2][kE * kF], bias[5][kE], act[kRows][kE + 1];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < e * e; i += blockDim.x) { W[0][i] = p.W1[i]; W[1][i] = p.W2[i]; W[2][i] = p.W3[i]; }
+    for (int i = tid; i < e * F; i += blockDim.x) { Wi[0][i] = p.Wd[i]; Wi[1][i] = p.Ww[i]; }
+    if (tid < e) { bias[0][tid] = p.bd[tid]; bias[1][tid] = p.bw[tid]; bias[2][tid] = p.b1[tid]; bias[3][tid] = p.b2[tid]; bias[4][tid] = p.b3[tid]; }
+    __syncthreads();
+    const int rl = tid / kE, u = tid % kE;
+    const int r = blockIdx.x * kRows + rl;
+    const bool on = r < R && u < e;
+    float v = 0.f;
+    if (on) {
+        v = bias[0][u] + bias[1][u];
+        for (int f = 0; f < F; ++f) v = fmaf(a[(long)r * in_stride + f], Wi[0][u * F + f], fmaf(b[(long)r * in_stride + f], Wi[1][u * F + f], v));
+        h0[(long)r * e + u] = v;
+    }
+    act[rl][u] = v;
+    __syncthreads();
+    float y = 0.f;
+    if (on) {
+        y = bias[2][u];
+        for (int k = 0; k < e; ++k) y = fmaf(act[rl][k], W[0][u * e + k], y);
+        z1[(long)r * e + u] = y;
+    }
+    __syncthreads();
+    act[rl][u] = fmaxf(y, 0.f);
+    __syncthreads();
+    if (on) {
+        y = bias[3][u];
+        for (int k = 0; k < e; ++k) y = fmaf(act[rl][k], W[1][u * e + k], y);
+        z2[(long)r * e + u] = y;
+    }
+    __syncthreads();
+    act[rl][u] = fmaxf(y, 0.f);
+    __syncthreads();
+    if (on) {
+        y = bias[4][u];
+        for (int k = 0; k < e; ++k) y = fmaf(act[rl][k], W[2][u * e + k], y);
+        out[(long)r * e + u] = y;
+    }
+}
+
+// packed gradient layout (per row chunk): dW3 e*e | db3 e | dW2 e*e | db2 e | dW1 e*e | db1 e | dWd e*F | dbd e | dWw e*F | dbw e
+__host__ __device__ inline int mlp_grad_floats(int e, int F) { return 3 * (e * e + e) + 2 * (e * F + e); }
+
+__global__ void __launch_bounds__(kRows* kE) time_mlp_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, MlpParams p,
+                                                                const float* __restrict__ h0, const float* __restrict__ z1,
+                                                                const float* __restrict__ z2, const float* __restrict__ g,
+                                                                float* __restrict__ part, int R, int F, int e, long in_stride) {
+    __shared__ float W[3][kE * kE];
+    __shared__ float G[kRows][kE + 1], A2[kRows][kE + 1], D2[kRows][kE + 1], A1[kRows][kE + 1], D1[kRows][kE + 1], H0[kRows][kE + 1],
+        DH[kRows][kE + 1];
+    __shared__ float Ain[kRows][kF], Bin[kRows][kF];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < e * e; i += blockDim.x) { W[0][i] = p.W1[i]; W[1][i] = p.W2[i]; W[2][i] = p.W3[i]; }
+    const int rl = tid / kE, u = tid % kE;
+    const int r = blockIdx.x * kRows + rl;
+    const bool on = r < R && u < e;
+    float zz1 = 0.f, zz2 = 0.f;
+    if (on) { zz1 = z1[(long)r * e + u]; zz2 = z2[(long)r * e + u]; }
+    G[rl][u] = on ? g[(long)r * e + u] : 0.f;
+    A2[rl][u] = fmaxf(zz2, 0.f);
+    A1[rl][u] = fmaxf(zz1, 0.f);
+    H0[rl][u] = on ? h0[(long)r * e + u] : 0.f;
+    if (u < F) {
+        Ain[rl][u] = (r < R) ? a[(long)r * in_stride + u] : 0.f;
+        Bin[rl][u] = (r < R) ? b[(long)r * in_stride + u] : 0.f;
+    }
+    __syncthreads();
+    // dz2 = (g W3) * (z2 > 0)
+    float d = 0.f;
+    if (on) { for (int k = 0; k < e; ++k) d = fmaf(G[rl][k], W[2][k * e + u], d); d = zz2 > 0.f ? d : 0.f; }
+    D2[rl][u] = d;
+    __syncthreads();
+    d = 0.f;
+    if (on) { for (int k = 0; k < e; ++k) d = fmaf(D2[rl][k], W[1][k * e + u], d); d = zz1 > 0.f ? d : 0.f; }
+    D1[rl][u] = d;
+    __syncthreads();
+    d = 0.f;
+    if (on) for (int k = 0; k < e; ++k) d = fmaf(D1[rl][k], W[0][k * e + u], d);
+    DH[rl][u] = d;
+    __syncthreads();
+    // parameter-gradient partials of this row chunk: one output element per thread (looped), fixed row order
+    float* out = part + (size_t)blockIdx.x * mlp_grad_floats(e, F);
+    const int nW = e * e, nI = e * F;
+    const int total = mlp_grad_floats(e, F);
+    for (int i = tid; i < total; i += blockDim.x) {
+        int o = i;
+        float s = 0.f;
+        // segment decoding
+        const float (*L)[kE + 1] = nullptr;      // left factor (delta), indexed [row][unit i]
+        const float (*Rt)[kE + 1] = nullptr;     // right factor (activation), indexed [row][unit j]
+        int mode = -1, ii = 0, jj = 0;           // 0: e x e outer product, 1: bias, 2: input a, 3: input b
+        if (o < nW) { L = G; Rt = A2; mode = 0; ii = o / e; jj = o % e; }
+        else if ((o -= nW) < e) { L = G; mode = 1; ii = o; }
+        else if ((o -= e) < nW) { L = D2; Rt = A1; mode = 0; ii = o / e; jj = o % e; }
+        else if ((o -= nW) < e) { L = D2; mode = 1; ii = o; }
+        else if ((o -= e) < nW) { L = D1; Rt = H0; mode = 0; ii = o / e; jj = o % e; }
+        else if ((o -= nW) < e) { L = D1; mode = 1; ii = o; }
+        else if ((o -= e) < nI) { L = DH; mode = 2; ii = o / F; jj = o % F; }
+        else if ((o -= nI) < e) { L = DH; mode = 1; ii = o; }
+        else if ((o -= e) < nI) { L = DH; mode = 3; ii = o / F; jj = o % F; }
+        else { o -= nI; L = DH; mode = 1; ii = o; }
+        for (int rr = 0; rr < kRows; ++rr) {
+            const float l = L[rr][ii];
+            const float rv = (mode == 0) ? Rt[rr][jj] : (mode == 1) ? 1.f : (mode == 2) ? Ain[rr][jj] : Bin[rr][jj];
+            s = fmaf(l, rv, s);
+        }
+        out[i] = s;
+    }
+}
+
+// dw/db partials of y = x w + b (one input feature): grid CTAs over row ranges, 256 threads = 4 row lanes x 64 columns
+__global__ void __launch_bounds__(256) affine1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                          float* __restrict__ part, long n, int D, long rows_per_cta) {
+    __shared__ float red[2][4][128];
+    const int tid = threadIdx.x, lane_r = tid / 64, c = tid % 64;
+    const long r0 = (long)blockIdx.x * rows_per_cta;
+    long r1 = r0 + rows_per_cta;
+    if (r1 > n) r1 = n;
+    for (int c0 = 0; c0 < D; c0 += 64) {
+        float sw = 0.f, sb = 0.f;
+        if (c0 + c < D) {
+            for (long r = r0 + lane_r; r < r1; r += 4) {
+                const float v = dy[r * D + c0 + c];
+                sw = fmaf(v, x[r], sw);
+                sb += v;
+            }
+        }
+        red[0][lane_r][c] = sw;
+        red[1][lane_r][c] = sb;
+        __syncthreads();
+        if (lane_r == 0 && c0 + c < D) {
+            part[((size_t)blockIdx.x * 2 + 0) * D + c0 + c] = (red[0][0][c] + red[0][1][c]) + (red[0][2][c] + red[0][3][c]);
+            part[((size_t)blockIdx.x * 2 + 1) * D + c0 + c] = (red[1][0][c] + red[1][1][c]) + (red[1][2][c] + red[1][3][c]);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace sm
+}  // namespace gptst
+
+using namespace gptst;
+
+extern "C" int gptst_time_mlp_chunks(int R) { return (R + sm::kRows - 1) / sm::kRows; }
+extern "C" int gptst_time_mlp_grad_floats(int e, int F) { return sm::mlp_grad_floats(e, F); }
+
+// a, b: (R, F) with row stride in_stride floats; weights as nn.Linear stores them ([out][in]); h0, z1, z2, out: (R, e)
+extern "C" int gptst_time_mlp_fwd(const float* a, const float* b, const float* Wd, const float* bd, const float* Ww,
+                                  const float* bw, const float* W1, const float* b1, const float* W2, const float* b2,
+                                  const float* W3, const float* b3, float* h0, float* z1, float* z2, float* out, int R, int F,
+                                  int e, long in_stride, void* stream) {
+    if (!a || !b || !Wd || !bd || !Ww || !bw || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !h0 || !z1 || !z2 || !out || R <= 0) return -1;
+    if (e < 1 || e > sm::kE || F < 1 || F > sm::kF) return -2;
+    sm::MlpParams p{Wd, bd, Ww, bw, W1, b1, W2, b2, W3, b3};
+    sm::time_mlp_fwd_kernel<<<gptst_time_mlp_chunks(R), sm::kRows * sm::kE, 0, (cudaStream_t)stream>>>(a, b, p, h0, z1, z2, out, R, F,
+                                                                                                     e, in_stride);
+    return (int)cudaGetLastError();
+}
+
+// g: (R, e) upstream gradient; part: (gptst_time_mlp_chunks(R), gptst_time_mlp_grad_floats(e, F)) partials, summed by the caller
+extern "C" int gptst_time_mlp_bwd(const float* a, const float* b, const float* W1, const float* W2, const float* W3,
+                                  const float* h0, const float* z1, const float* z2, const float* g, float* part, int R, int F,
+                                  int e, long in_stride, void* stream) {
+    if (!a || !b || !W1 || !W2 || !W3 || !h0 || !z1 || !z2 || !g || !part || R <= 0) return -1;
+    if (e < 1 || e > sm::kE || F < 1 || F > sm::kF) return -2;
+    sm::MlpParams p{nullptr, nullptr, nullptr, nullptr, W1, nullptr, W2, nullptr, W3, nullptr};
+    sm::time_mlp_bwd_kernel<<<gptst_time_mlp_chunks(R), sm::kRows * sm::kE, 0, (cudaStream_t)stream>>>(a, b, p, h0, z1, z2, g, part, R,
+                                                                                                     F, e, in_stride);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int gptst_affine1_bwd_parts(long n) {
+    long want = 2 * 148;
+    if (want > (n + 255) / 256) want = (n + 255) / 256;
+    return (int)(want < 1 ? 1 : want);
+}
+// part: (parts, 2, D): [p][0] = partial dw, [p][1] = partial db
+extern "C" int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream) {
+    if (!dy || !x || !part || n <= 0 || parts <= 0) return -1;
+    if (D < 1 || D > 1024) return -2;
+    const long rpc = (n + parts - 1) / parts;
+    sm::affine1_bwd_kernel<<<parts, 256, 0, (cudaStream_t)stream>>>(dy, x, part, n, D, rpc);
+    return (int)cudaGetLastError();
+}

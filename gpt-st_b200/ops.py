@@ -279,6 +279,79 @@ def time_adaptive_proj(x, Wt, bt, prec=None):
 
 
 # ---------------------------------------------------------------------------------------------------
+# small parameter-side ops (time-embedding MLP, one-feature input embedding)
+# ---------------------------------------------------------------------------------------------------
+class _TimeMLP(torch.autograd.Function):
+    """time_feature / time_feature_spg (GPTST.py:187-219) as one forward and one backward kernel.  ab: (2, R, F) contiguous
+    (the day / week inputs), weights as the nn.Linear modules hold them."""
+
+    @staticmethod
+    def forward(ctx, ab, Wd, bd, Ww, bw, W1, b1, W2, b2, W3, b3):
+        ab = ab.contiguous()
+        ps = [t.contiguous() for t in (Wd, bd, Ww, bw, W1, b1, W2, b2, W3, b3)]
+        _chk(ab, *ps)
+        _, R, F = ab.shape
+        e = W1.shape[0]
+        dev = ab.device
+        h0, z1, z2, out = (torch.empty((R, e), device=dev, dtype=torch.float32) for _ in range(4))
+        a, b = ab[0], ab[1]
+        rc = _lib.lib().gptst_time_mlp_fwd(_p(a), _p(b), *[_p(t) for t in ps], _p(h0), _p(z1), _p(z2), _p(out), R, F, e, F, _stream())
+        _lib.check(rc, "gptst_time_mlp_fwd")
+        ctx.save_for_backward(ab, ps[4], ps[6], ps[8], h0, z1, z2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ab, W1, W2, W3, h0, z1, z2 = ctx.saved_tensors
+        _, R, F = ab.shape
+        e = W1.shape[0]
+        L = _lib.lib()
+        chunks, nf = L.gptst_time_mlp_chunks(R), L.gptst_time_mlp_grad_floats(e, F)
+        part = torch.empty((chunks, nf), device=ab.device, dtype=torch.float32)
+        rc = L.gptst_time_mlp_bwd(_p(ab[0]), _p(ab[1]), _p(W1), _p(W2), _p(W3), _p(h0), _p(z1), _p(z2), _p(g.contiguous()), _p(part), R, F,
+                                  e, F, _stream())
+        _lib.check(rc, "gptst_time_mlp_bwd")
+        tot = part[0] if chunks == 1 else part.sum(0)
+        sizes = [e * e, e, e * e, e, e * e, e, e * F, e, e * F, e]
+        dW3, db3, dW2, db2, dW1, db1, dWd, dbd, dWw, dbw = torch.split(tot, sizes)
+        return (None, dWd.view(e, F), dbd, dWw.view(e, F), dbw, dW1.view(e, e), db1, dW2.view(e, e), db2, dW3.view(e, e), db3)
+
+
+def time_mlp(ab, mod):
+    """mod: a time_feature module (ln_day, ln_week, ln1, ln2, ln); ab (2, R, F)."""
+    return _TimeMLP.apply(ab, mod.ln_day.weight, mod.ln_day.bias, mod.ln_week.weight, mod.ln_week.bias, mod.ln1.weight, mod.ln1.bias,
+                          mod.ln2.weight, mod.ln2.bias, mod.ln.weight, mod.ln.bias)
+
+
+class _Affine1(torch.autograd.Function):
+    """y = x w + b for a linear layer with ONE input feature; the backward is a single pass over dy."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addcmul(bias, x, weight.view(-1))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        _chk(dy)
+        D = dy.shape[-1]
+        n = dy.numel() // D
+        L = _lib.lib()
+        parts = L.gptst_affine1_bwd_parts(n)
+        part = torch.empty((parts, 2, D), device=dy.device, dtype=torch.float32)
+        _lib.check(L.gptst_affine1_bwd(_p(dy), _p(x.contiguous()), _p(part), n, D, parts, _stream()), "gptst_affine1_bwd")
+        tot = part.sum(0)
+        dx = (dy * weight.view(-1)).sum(-1, keepdim=True) if ctx.needs_input_grad[0] else None
+        return dx, tot[0].view_as(weight), tot[1]
+
+
+def affine1(x, weight, bias):
+    return _Affine1.apply(x, weight, bias)
+
+
+# ---------------------------------------------------------------------------------------------------
 # on-device mask construction (row f1)
 # ---------------------------------------------------------------------------------------------------
 def mask_labels(prob):

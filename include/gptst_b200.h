@@ -126,6 +126,23 @@ int gptst_mask_adaptive(const float* prob, const unsigned char* label_in, const 
                         int H, int i0, int all_type, void* stream);
 int gptst_mask_random(const long long* k_dev, const float* u, int* ws, long long* final_mask, long n, void* stream);
 
+/* ---- small parameter-side ops that sat on the critical tail of the captured step as chains of tiny library kernels -------
+ * time_mlp: the time-embedding MLP of GPTST.py:187-219 (h0 = a Wd^T + bd + b Ww^T + bw; z1 = h0 W1^T + b1; z2 = relu(z1) W2^T + b2;
+ * out = relu(z2) W3^T + b3) on R rows with F inputs per branch (row stride in_stride) and e <= 16 units; weights [out][in].
+ * backward writes (gptst_time_mlp_chunks(R), gptst_time_mlp_grad_floats(e,F)) partials packed as
+ * dW3 | db3 | dW2 | db2 | dW1 | db1 | dWd | dbd | dWw | dbw, summed by the caller.
+ * affine1_bwd: y = x w + b with one input feature (GPTST.py:22, :298): part[p][0] = partial sum_i dy[i,:] x[i], part[p][1] = partial sum_i dy[i,:]. */
+int gptst_time_mlp_chunks(int R);
+int gptst_time_mlp_grad_floats(int e, int F);
+int gptst_time_mlp_fwd(const float* a, const float* b, const float* Wd, const float* bd, const float* Ww, const float* bw,
+                       const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                       float* h0, float* z1, float* z2, float* out, int R, int F, int e, long in_stride, void* stream);
+int gptst_time_mlp_bwd(const float* a, const float* b, const float* W1, const float* W2, const float* W3, const float* h0,
+                       const float* z1, const float* z2, const float* g, float* part, int R, int F, int e, long in_stride,
+                       void* stream);
+int gptst_affine1_bwd_parts(long n);
+int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
+
 /* ---- fused pre-training loss + analytic gradients ------------------------------------
  * mode 0: probe loss mean|(o - x)*m| ; mode 1: masked MAE of Run.py:91-101 / lib/metrics.py:11-18 (inverse z-score with
  * mean/std, keep true*m > thr) ; plus kl_w * KLDivLoss(sum)(log prob, hs) (BasicTrainer.py:84-86) when kl_w != 0.

@@ -355,3 +355,43 @@ def test_mask_random_phase_kernel():
         want = _exact_count_mask(u, k)
         assert torch.equal(ops.mask_select_random(u, kd), want), ("one-CTA", n, k, quant)
         assert torch.equal(ops.mask_random(u, kd), want), ("pipeline", n, k, quant)
+
+
+@pytest.mark.parametrize("kind,e", [("tf", 16), ("tf", 4), ("spg", 4)])
+def test_time_mlp_fused_matches_torch(kind, e):
+    """time_feature / time_feature_spg (GPTST.py:187-219): fused forward/backward kernels vs the plain nn.Linear stack."""
+    from gptst_b200.GPTST import time_feature, time_feature_spg
+    torch.manual_seed(3)
+    B, T = 5, 12
+    mod = (time_feature(e) if kind == "tf" else time_feature_spg(e)).double()
+    eb = torch.rand(B, T, 2, dtype=torch.float64)
+    if kind == "tf":
+        h = mod.ln_day(eb[:, :, 0:1]) + mod.ln_week(eb[:, :, 1:2])
+    else:
+        h = mod.ln_day(eb[:, :, 0]) + mod.ln_week(eb[:, :, 1])
+    want = mod.ln(torch.relu(mod.ln2(torch.relu(mod.ln1(h)))))
+    g = torch.randn_like(want)
+    want.backward(g)
+    ref = {k: p.grad.clone() for k, p in mod.named_parameters()}
+    cu = (time_feature(e) if kind == "tf" else time_feature_spg(e)).cuda()
+    cu.load_state_dict({k: v.float() for k, v in mod.state_dict().items()})
+    got = cu(eb.float().cuda())
+    check(got, want, 2e-6, "time mlp out")
+    got.backward(g.float().cuda())
+    for k, p in cu.named_parameters():
+        check(p.grad, ref[k], 1e-5, "time mlp grad " + k)
+
+
+def test_affine1_matches_linear():
+    from gptst_b200 import ops
+    lin = torch.nn.Linear(1, 64).double()
+    x = torch.randn(3, 12, 37, 1, dtype=torch.float64)
+    want = lin(x)
+    g = torch.randn_like(want)
+    want.backward(g)
+    w, b = lin.weight.detach().float().cuda().requires_grad_(), lin.bias.detach().float().cuda().requires_grad_()
+    got = ops.affine1(x.float().cuda(), w, b)
+    check(got, want, 1e-6, "affine1 out")
+    got.backward(g.float().cuda())
+    check(w.grad, lin.weight.grad, 5e-6, "affine1 dw")
+    check(b.grad, lin.bias.grad, 5e-6, "affine1 db")
