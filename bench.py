@@ -259,8 +259,47 @@ def hypertem_forward_time(N, D, B, iters=20):
     return 8 * B * T_STEPS * N * D, statistics.median(times)
 
 
+def kernel_rooflines(N, D, B, peak, iters=20):
+    """The two kernels that dominate the step (gptst_gproj_bwd time-grouped = hyperTem's projection backward, 8 launches, and
+    gptst_tmix_bwd, 8 launches) timed alone with CUDA events on rotating buffer sets > L2, against their algorithmic bytes."""
+    from gptst_b200 import ops
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    A = 4 * B * T_STEPS * N * D
+    nset = max(3, int(400e6 // (5 * A)) + 1)
+    sets = [[torch.randn(B, T_STEPS, N, D, device=dev, generator=g) for _ in range(4)] for _ in range(nset)]
+    W = torch.randn(B, 12, D, D, device=dev, generator=g) * D ** -0.5
+    Mn = torch.randn(N, 12, 12, device=dev, generator=g) * 0.2
+    prec = ops.default_precision()
+    out = {}
+
+    def timeit(fn):
+        ts = []
+        for i in range(3 + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(sets[i % nset])
+            e1.record()
+            e1.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    with torch.no_grad():
+        # the call also sums its (splits == 1) partials: a view, no extra kernel
+        ms = timeit(lambda s: ops.gproj_bwd(s[0], s[1], s[2], W, node_grouped=False, act=True, prec=prec, want_dres=True))
+        algo = 5 * A + 2 * 4 * B * 12 * D * D     # dY, Y, X in; dX, dRes out; W_bt in, dW_bt out
+        out["gproj_bwd_time_grouped"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
+                                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
+        ms = timeit(lambda s: ops.tmix_bwd(s[0], s[1], Mn, s[2], prec))
+        algo = 4 * A                              # dy, x in; dx read-modify-write
+        out["tmix_bwd"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
+                           "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
+    return out
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one cap forward, from the committed
-# `ncu --set full` capture (profiles/ncu_cap_forward_r01.md); only known for the geometry that was captured.
+# `ncu --set full` capture (profiles/ncu_cap_forward_r01_b.md); only known for the geometry that was captured.
 NCU_TRAFFIC_BYTES = {("pems08", 64): 124.8e6}
 
 
@@ -365,11 +404,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "step_mode": "eager" if args.eager else "one CUDA graph per step (gptst_b200.train.PretrainStep)",
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + cap_hop_fwd + cap_recon + gproj_fwd), "
-                         "the hypergraph + node-adaptive GCN block", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + gptst_cap_hop_e1 + gptst_cap_recon_hop + "
+                         "gptst_gproj_fwd), the hypergraph + node-adaptive GCN block named by BASELINE.json", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, B)), "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
             "roofline_hypertem_fwd": {"achieved": ht_algo / (ht_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ht_ms,
                                       "algorithmic_bytes": ht_algo, "frac": ht_algo / (ht_ms * 1e-3) / 1e9 / peak},
+            "roofline_kernels": kernel_rooflines(N, D, B, peak),
             "step_roofline": {"algorithmic_bytes": step_bytes, "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
             "last_loss": last_loss,
         }

@@ -56,10 +56,10 @@ class MLP_RL(nn.Module):
         self.device = device
 
     def tables_spa(self, node_eb):
-        return torch.einsum("nd,dio->nio", node_eb, self.weights_pool_spa), node_eb @ self.bias_pool_spa
+        return ops.lowrank_table(node_eb, self.weights_pool_spa), ops.lowrank_table(node_eb, self.bias_pool_spa)
 
     def tables_tem(self, time_eb):
-        return torch.einsum("btd,dio->btio", time_eb, self.weights_pool_tem), time_eb @ self.bias_pool_tem
+        return ops.lowrank_table(time_eb, self.weights_pool_tem), ops.lowrank_table(time_eb, self.bias_pool_tem)
 
     def forward(self, eb, time_eb, node_eb, tables=None):
         """tables = ((Wn, bn, event), (Wt, bt, event)) when the caller produced them on side streams."""
@@ -97,10 +97,10 @@ class cap(nn.Module):
         """Parameter-side contractions (independent of x): incidence logits, inter-cluster adjacency, node-adaptive weights."""
         if self.timesteps != 12:
             raise RuntimeError("cap: the reference (and the kernels) hard-wire 12 time steps")
-        dadj = torch.einsum("btd,dhn->bthn", teb, self.adj)
-        dyn = torch.einsum("bd,dhk->bhk", time_eb, self.t_adj)
-        Wn = torch.einsum("nd,dio->nio", node_embeddings, self.weights_spa)
-        bn = node_embeddings @ self.bias_spa
+        dadj = ops.lowrank_table(teb, self.adj)                         # einsum("btd,dhn->bthn")
+        dyn = ops.lowrank_table(time_eb, self.t_adj)                    # einsum("bd,dhk->bhk")
+        Wn = ops.lowrank_table(node_embeddings, self.weights_spa)       # einsum("nd,dio->nio")
+        bn = ops.lowrank_table(node_embeddings, self.bias_spa)
         return dadj, dyn, Wn, bn
 
     def forward(self, x, node_embeddings, time_eb, teb, tables=None):
@@ -121,10 +121,10 @@ class hyperTem(nn.Module):
 
     def tables(self, node_embeddings, time_eb):
         """Parameter-side contractions (independent of eb): per-node T x T mix and time-adaptive weights."""
-        A = torch.einsum("nk,kht->nht", node_embeddings, self.adj)
+        A = ops.lowrank_table(node_embeddings, self.adj)                # einsum("nk,kht->nht")
         Mn = torch.einsum("nht,nhs->nts", A, A)                      # two hops with no nonlinearity in between
-        W = torch.einsum("btd,dio->btio", time_eb, self.weights_pool)
-        bias = time_eb @ self.bias_pool
+        W = ops.lowrank_table(time_eb, self.weights_pool)               # einsum("btd,dio->btio")
+        bias = ops.lowrank_table(time_eb, self.bias_pool)
         return Mn, W, bias
 
     def forward(self, eb, node_embeddings, time_eb, tables=None):

@@ -212,3 +212,113 @@ extern "C" int gptst_affine1_bwd(const float* dy, const float* x, float* part, l
     sm::affine1_bwd_kernel<<<parts, 256, 0, (cudaStream_t)stream>>>(dy, x, part, n, D, rpc);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the low-rank table generators  Tab = te . pool  (te (G,d), pool (d,C), d <= 16): the adaptive weights
+// W_bt / W_n, their biases, the incidence logits dadj and the inter-cluster adjacency dyn are all of this form
+// (GPTST.py:104, :129, :137-138, :160-161, :24-31).  cuBLAS runs these skinny products (K = 768 or 170, M = 16) with SIMT
+// split-K kernels at 15-90 us each; as plain streaming kernels they are a few microseconds:
+//     dpool[k][c] = sum_g te[g][k] dTab[g][c]      (column chunks of 32, 8 row lanes, te staged in shared memory)
+//     dte[g][k]   = sum_c dTab[g][c] pool[k][c]    (4 rows per CTA, threads stride over the columns)
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+
+constexpr int kDmax = 16;
+
+__global__ void __launch_bounds__(256) table_dpool_kernel(const float* __restrict__ te, const float* __restrict__ dtab,
+                                                          float* __restrict__ dpool, int G, int d, int C) {
+    extern __shared__ float tes[];                 // [G][d]
+    __shared__ float red[8][32][kDmax + 1];
+    const int tid = threadIdx.x, cl = tid & 31, rl = tid >> 5;
+    for (int i = tid; i < G * d; i += 256) tes[i] = te[i];
+    __syncthreads();
+    const int c = blockIdx.x * 32 + cl;
+    float acc[kDmax];
+#pragma unroll
+    for (int k = 0; k < kDmax; ++k) acc[k] = 0.f;
+    if (c < C) {
+        for (int g = rl; g < G; g += 8) {
+            const float v = dtab[(size_t)g * C + c];
+            const float* t = tes + g * d;
+#pragma unroll
+            for (int k = 0; k < kDmax; ++k)
+                if (k < d) acc[k] = fmaf(t[k], v, acc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kDmax; ++k) red[rl][cl][k] = acc[k];
+    __syncthreads();
+    for (int i = tid; i < 32 * d; i += 256) {
+        const int k = i / 32, cc = i % 32;
+        if (blockIdx.x * 32 + cc < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) s += red[r][cc][k];
+            dpool[(size_t)k * C + blockIdx.x * 32 + cc] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) table_dte_kernel(const float* __restrict__ pool, const float* __restrict__ dtab,
+                                                        float* __restrict__ dte, int G, int d, int C) {
+    __shared__ float red[8][4][kDmax];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g0 = blockIdx.x * 4;
+    float acc[4][kDmax];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < kDmax; ++k) acc[r][k] = 0.f;
+    for (int c = tid; c < C; c += 256) {
+        float v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = (g0 + r < G) ? dtab[(size_t)(g0 + r) * C + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kDmax; ++k) {
+            if (k < d) {
+                const float p = pool[(size_t)k * C + c];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r][k] = fmaf(v[r], p, acc[r][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < kDmax; ++k) {
+            float s = acc[r][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[warp][r][k] = s;
+        }
+    __syncthreads();
+    if (tid < 4 * kDmax) {
+        const int r = tid / kDmax, k = tid % kDmax;
+        if (g0 + r < G && k < d) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][r][k];
+            dte[(size_t)(g0 + r) * d + k] = s;
+        }
+    }
+}
+
+}  // namespace sm
+}  // namespace gptst
+
+// te (G,d), pool (d,C), dtab (G,C) -> dpool (d,C), dte (G,d); either output may be NULL
+extern "C" int gptst_table_bwd(const float* te, const float* pool, const float* dtab, float* dpool, float* dte, int G, int d,
+                               int C, void* stream) {
+    if (!te || !pool || !dtab || G <= 0 || C <= 0) return -1;
+    if (d < 1 || d > gptst::sm::kDmax || (size_t)G * d * 4 > 160 * 1024) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dpool) {
+        const size_t smem = (size_t)G * d * 4;
+        cudaError_t e = cudaFuncSetAttribute(gptst::sm::table_dpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        gptst::sm::table_dpool_kernel<<<(C + 31) / 32, 256, smem, st>>>(te, dtab, dpool, G, d, C);
+    }
+    if (dte) gptst::sm::table_dte_kernel<<<(G + 3) / 4, 256, 0, st>>>(pool, dtab, dte, G, d, C);
+    return (int)cudaGetLastError();
+}

@@ -323,6 +323,41 @@ def time_mlp(ab, mod):
                           mod.ln2.weight, mod.ln2.bias, mod.ln.weight, mod.ln.bias)
 
 
+class _LowRankTable(torch.autograd.Function):
+    """Tab = te . pool with te (G, d), pool (d, C), d <= 16: the generators of every adaptive table of the model.  Forward is
+    a plain matmul (off the critical path, on the prologue streams); the backward pair of skinny products runs as two
+    streaming kernels instead of cuBLAS SIMT split-K GEMMs."""
+
+    @staticmethod
+    def forward(ctx, te, pool):
+        ctx.save_for_backward(te, pool)
+        return te @ pool
+
+    @staticmethod
+    def backward(ctx, dtab):
+        te, pool = ctx.saved_tensors
+        te, pool, dtab = te.contiguous(), pool.contiguous(), dtab.contiguous()
+        _chk(te, pool, dtab)
+        G, d = te.shape
+        C = pool.shape[1]
+        dpool = torch.empty_like(pool) if ctx.needs_input_grad[1] else None
+        dte = torch.empty_like(te) if ctx.needs_input_grad[0] else None
+        st = _stream()
+        if dpool is not None and dte is not None:
+            _count(1)
+        _lib.check(_lib.lib().gptst_table_bwd(_p(te), _p(pool), _p(dtab), _p(dpool), _p(dte), G, d, C, st), "gptst_table_bwd")
+        return dte, dpool
+
+
+def lowrank_table(te, pool):
+    """te (..., d) x pool (d, ...) -> (te.shape[:-1] + pool.shape[1:]); einsum('...d,d***->...***')."""
+    d = te.shape[-1]
+    if d > 16 or not te.is_cuda:
+        return (te.reshape(-1, d) @ pool.reshape(d, -1)).view(te.shape[:-1] + pool.shape[1:])
+    out = _LowRankTable.apply(te.reshape(-1, d), pool.reshape(d, -1))
+    return out.view(te.shape[:-1] + pool.shape[1:])
+
+
 class _Affine1(torch.autograd.Function):
     """y = x w + b for a linear layer with ONE input feature; the backward is a single pass over dy."""
 

@@ -395,3 +395,16 @@ def test_affine1_matches_linear():
     got.backward(g.float().cuda())
     check(w.grad, lin.weight.grad, 5e-6, "affine1 dw")
     check(b.grad, lin.bias.grad, 5e-6, "affine1 db")
+
+
+@pytest.mark.parametrize("G,d,C", [(768, 16, 4096), (170, 16, 64), (36, 4, 1700), (5, 4, 1920), (7, 16, 100)])
+def test_lowrank_table_backward(G, d, C):
+    from gptst_b200 import ops
+    te, pool, g = rnd(G, d, seed=1).requires_grad_(), rnd(d, C, seed=2).requires_grad_(), rnd(G, C, seed=3)
+    (te @ pool).backward(g)
+    tc, pc = te.detach().float().cuda().requires_grad_(), pool.detach().float().cuda().requires_grad_()
+    out = ops.lowrank_table(tc, pc)
+    check(out, (te @ pool).detach(), 2e-6, "table")
+    out.backward(g.float().cuda())
+    check(tc.grad, te.grad, 5e-6, "table dte")
+    check(pc.grad, pool.grad, 5e-6, "table dpool")
