@@ -226,35 +226,43 @@ namespace sm {
 
 constexpr int kDmax = 16;
 
-__global__ void __launch_bounds__(256) table_dpool_kernel(const float* __restrict__ te, const float* __restrict__ dtab,
-                                                          float* __restrict__ dpool, int G, int d, int C) {
-    extern __shared__ float tes[];                 // [G][d]
-    __shared__ float red[8][32][kDmax + 1];
+// 1024 threads = 32 columns x 32 row lanes (the first version had 8 row lanes: ~7 warps per SM, latency-bound at 24-37 us)
+__global__ void __launch_bounds__(1024) table_dpool_kernel(const float* __restrict__ te, const float* __restrict__ dtab,
+                                                           float* __restrict__ dpool, int G, int d, int C) {
+    extern __shared__ __align__(16) float tes[];   // [G][16] (rows padded to 16 floats), then red[32][32][17]
+    float* red = tes + (size_t)G * kDmax;
     const int tid = threadIdx.x, cl = tid & 31, rl = tid >> 5;
-    for (int i = tid; i < G * d; i += 256) tes[i] = te[i];
+    for (int i = tid; i < G * kDmax; i += 1024) {
+        const int g = i / kDmax, k = i % kDmax;
+        tes[i] = (k < d) ? te[(size_t)g * d + k] : 0.f;
+    }
     __syncthreads();
     const int c = blockIdx.x * 32 + cl;
     float acc[kDmax];
 #pragma unroll
     for (int k = 0; k < kDmax; ++k) acc[k] = 0.f;
     if (c < C) {
-        for (int g = rl; g < G; g += 8) {
+#pragma unroll 4
+        for (int g = rl; g < G; g += 32) {
             const float v = dtab[(size_t)g * C + c];
-            const float* t = tes + g * d;
+            const float4* t4 = reinterpret_cast<const float4*>(tes + (size_t)g * kDmax);
 #pragma unroll
-            for (int k = 0; k < kDmax; ++k)
-                if (k < d) acc[k] = fmaf(t[k], v, acc[k]);
+            for (int q = 0; q < kDmax / 4; ++q) {
+                const float4 t = t4[q];
+                acc[4 * q] = fmaf(t.x, v, acc[4 * q]); acc[4 * q + 1] = fmaf(t.y, v, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(t.z, v, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(t.w, v, acc[4 * q + 3]);
+            }
         }
     }
 #pragma unroll
-    for (int k = 0; k < kDmax; ++k) red[rl][cl][k] = acc[k];
+    for (int k = 0; k < kDmax; ++k) red[((size_t)rl * 32 + cl) * (kDmax + 1) + k] = acc[k];
     __syncthreads();
-    for (int i = tid; i < 32 * d; i += 256) {
+    for (int i = tid; i < 32 * d; i += 1024) {
         const int k = i / 32, cc = i % 32;
         if (blockIdx.x * 32 + cc < C) {
             float s = 0.f;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) s += red[r][cc][k];
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) s += red[((size_t)r * 32 + cc) * (kDmax + 1) + k];
             dpool[(size_t)k * C + blockIdx.x * 32 + cc] = s;
         }
     }
@@ -311,13 +319,13 @@ __global__ void __launch_bounds__(256) table_dte_kernel(const float* __restrict_
 extern "C" int gptst_table_bwd(const float* te, const float* pool, const float* dtab, float* dpool, float* dte, int G, int d,
                                int C, void* stream) {
     if (!te || !pool || !dtab || G <= 0 || C <= 0) return -1;
-    if (d < 1 || d > gptst::sm::kDmax || (size_t)G * d * 4 > 160 * 1024) return -2;
+    if (d < 1 || d > gptst::sm::kDmax || (size_t)G * gptst::sm::kDmax * 4 > 140 * 1024) return -2;
     cudaStream_t st = (cudaStream_t)stream;
     if (dpool) {
-        const size_t smem = (size_t)G * d * 4;
+        const size_t smem = ((size_t)G * gptst::sm::kDmax + 32 * 32 * (gptst::sm::kDmax + 1)) * 4;
         cudaError_t e = cudaFuncSetAttribute(gptst::sm::table_dpool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        gptst::sm::table_dpool_kernel<<<(C + 31) / 32, 256, smem, st>>>(te, dtab, dpool, G, d, C);
+        gptst::sm::table_dpool_kernel<<<(C + 31) / 32, 1024, smem, st>>>(te, dtab, dpool, G, d, C);
     }
     if (dte) gptst::sm::table_dte_kernel<<<(G + 3) / 4, 256, 0, st>>>(pool, dtab, dte, G, d, C);
     return (int)cudaGetLastError();
