@@ -122,7 +122,7 @@ class hyperTem(nn.Module):
     def tables(self, node_embeddings, time_eb):
         """Parameter-side contractions (independent of eb): per-node T x T mix and time-adaptive weights."""
         A = ops.lowrank_table(node_embeddings, self.adj)                # einsum("nk,kht->nht")
-        Mn = torch.einsum("nht,nhs->nts", A, A)                      # two hops with no nonlinearity in between
+        Mn = ops.mix_matrix(A) if A.is_cuda else torch.einsum("nht,nhs->nts", A, A)   # two hops, no nonlinearity in between
         W = ops.lowrank_table(time_eb, self.weights_pool)               # einsum("btd,dio->btio")
         bias = ops.lowrank_table(time_eb, self.bias_pool)
         return Mn, W, bias

@@ -330,3 +330,196 @@ extern "C" int gptst_table_bwd(const float* te, const float* pool, const float* 
     if (dte) gptst::sm::table_dte_kernel<<<(G + 3) / 4, 256, 0, st>>>(pool, dtab, dte, G, d, C);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused backward of a low-rank table on the tensor cores: dTab is read ONCE.  CTA tile = 64 rows x 128 columns of dTab
+// (cp.async into shared memory); 3xTF32 mma.sync m16n8k8 (truncating split, common.cuh):
+//     dte partial  (rows of the tile, over its 128 columns) : M = 64 rows, N = 16, K = 128 -> dte_part[col chunk][G][16]
+//     dpool partial (columns of the tile, over its 64 rows) : M = 16,      N = 128, K = 64 -> dpool_part[row chunk][16][C]
+// The caller sums the partials (fixed order).  pool is re-read once per 64 rows (was once per 4), te once per 128 columns.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+
+constexpr int TR = 64, TC = 128, LDT = TC + 4, LDE = 20;   // LDT % 32 == 4, LDE: rows 2t hit banks 8t (+g)
+
+__global__ void __launch_bounds__(256) table_bwd_fused_kernel(const float* __restrict__ te, const float* __restrict__ pool,
+                                                              const float* __restrict__ dtab, float* __restrict__ dpool_part,
+                                                              float* __restrict__ dte_part, int G, int d, int C) {
+    extern __shared__ __align__(16) float smf[];
+    float* tile = smf;                          // [TR][LDT]
+    float* tes = tile + TR * LDT;               // [TR][LDE]  te rows of this chunk (columns >= d zero)
+    float* red = tes + TR * LDE;                // [4][16][17] second k-half of the dte product
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * TR, c0 = blockIdx.y * TC;
+    const bool vec_ok = (C % 4 == 0);
+    for (int i = tid; i < TR * (TC / 4); i += 256) {
+        const int r = i / (TC / 4), q = i % (TC / 4);
+        float* dst = tile + r * LDT + 4 * q;
+        const int gr = r0 + r, gc = c0 + 4 * q;
+        if (gr < G && gc + 3 < C && vec_ok) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                         "l"(dtab + (size_t)gr * C + gc) : "memory");
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[e] = (gr < G && gc + e < C) ? dtab[(size_t)gr * C + gc + e] : 0.f;
+        }
+    }
+    for (int i = tid; i < TR * 16; i += 256) {
+        const int r = i >> 4, k = i & 15;
+        tes[r * LDE + k] = (r0 + r < G && k < d) ? te[(size_t)(r0 + r) * d + k] : 0.f;
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    // ---- dte partial: warp = (m-tile mt = warp & 3 : rows 16mt.., k-half kh = warp >> 2 : columns 64kh..)
+    {
+        const int mt = warp & 3, kh = warp >> 2;
+        float acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        const float* arow0 = tile + (16 * mt + g) * LDT + 64 * kh;
+        const float* arow1 = arow0 + 8 * LDT;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int k0 = 8 * ks;
+            uint32_t ah[4], al[4];
+            split_tf32<PREC_3XTF32>(arow0[k0 + t], ah[0], al[0]);
+            split_tf32<PREC_3XTF32>(arow1[k0 + t], ah[1], al[1]);
+            split_tf32<PREC_3XTF32>(arow0[k0 + t + 4], ah[2], al[2]);
+            split_tf32<PREC_3XTF32>(arow1[k0 + t + 4], ah[3], al[3]);
+            const int gc = c0 + 64 * kh + k0 + t;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int kk = 8 * j + g;
+                const float p0 = (kk < d && gc < C) ? pool[(size_t)kk * C + gc] : 0.f;
+                const float p1 = (kk < d && gc + 4 < C) ? pool[(size_t)kk * C + gc + 4] : 0.f;
+                uint32_t bh[2], bl[2];
+                split_tf32<PREC_3XTF32>(p0, bh[0], bl[0]);
+                split_tf32<PREC_3XTF32>(p1, bh[1], bl[1]);
+                mma_split<PREC_3XTF32>(acc[j], ah, al, bh, bl);
+            }
+        }
+        // C fragment: (row g / g+8 of the m-tile, kk = 8j + 2t, 2t+1)
+        if (kh == 1) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                red[(mt * 16 + g) * 17 + 8 * j + 2 * t] = acc[j][0];
+                red[(mt * 16 + g) * 17 + 8 * j + 2 * t + 1] = acc[j][1];
+                red[(mt * 16 + g + 8) * 17 + 8 * j + 2 * t] = acc[j][2];
+                red[(mt * 16 + g + 8) * 17 + 8 * j + 2 * t + 1] = acc[j][3];
+            }
+        }
+        __syncthreads();
+        if (kh == 0) {
+            float* out = dte_part + (size_t)blockIdx.y * G * 16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int rl = mt * 16 + g + 8 * h, gr = r0 + rl;
+                    if (gr < G) {
+                        out[(size_t)gr * 16 + 8 * j + 2 * t] = acc[j][2 * h] + red[rl * 17 + 8 * j + 2 * t];
+                        out[(size_t)gr * 16 + 8 * j + 2 * t + 1] = acc[j][2 * h + 1] + red[rl * 17 + 8 * j + 2 * t + 1];
+                    }
+                }
+            }
+        }
+    }
+    // ---- dpool partial: warp owns column tiles 2*warp, 2*warp+1 (8 columns each); K = the tile's 64 rows, k index of an
+    //      8-step permuted as {t, t+4} <-> rows {2t, 2t+1} so that the B reads of the fp32 tile are conflict-free
+    {
+        float acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const int ra = 8 * ks + 2 * t, rb = ra + 1;
+            uint32_t ah[4], al[4];
+            split_tf32<PREC_3XTF32>(tes[ra * LDE + g], ah[0], al[0]);         // (m = kk g,     k = t)
+            split_tf32<PREC_3XTF32>(tes[ra * LDE + g + 8], ah[1], al[1]);     // (m = kk g + 8, k = t)
+            split_tf32<PREC_3XTF32>(tes[rb * LDE + g], ah[2], al[2]);         // (m = kk g,     k = t + 4)
+            split_tf32<PREC_3XTF32>(tes[rb * LDE + g + 8], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int cl = 8 * (2 * warp + j) + g;
+                uint32_t bh[2], bl[2];
+                split_tf32<PREC_3XTF32>(tile[ra * LDT + cl], bh[0], bl[0]);
+                split_tf32<PREC_3XTF32>(tile[rb * LDT + cl], bh[1], bl[1]);
+                mma_split<PREC_3XTF32>(acc[j], ah, al, bh, bl);
+            }
+        }
+        float* out = dpool_part + (size_t)blockIdx.x * 16 * C;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gc = c0 + 8 * (2 * warp + j) + 2 * t;      // C fragment: (kk = g / g+8, column 2t, 2t+1 of the tile)
+            if (gc < C) { out[(size_t)g * C + gc] = acc[j][0]; out[(size_t)(g + 8) * C + gc] = acc[j][2]; }
+            if (gc + 1 < C) { out[(size_t)g * C + gc + 1] = acc[j][1]; out[(size_t)(g + 8) * C + gc + 1] = acc[j][3]; }
+        }
+    }
+}
+
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_table_bwd2_chunks(int G, int C, int* row_chunks, int* col_chunks) {
+    if (!row_chunks || !col_chunks) return -1;
+    *row_chunks = (G + gptst::sm::TR - 1) / gptst::sm::TR;
+    *col_chunks = (C + gptst::sm::TC - 1) / gptst::sm::TC;
+    return 0;
+}
+// dpool_part: (row_chunks, 16, C), dte_part: (col_chunks, G, 16); rows kk >= d of dpool_part and columns >= d of dte_part are zero
+extern "C" int gptst_table_bwd2(const float* te, const float* pool, const float* dtab, float* dpool_part, float* dte_part, int G,
+                                int d, int C, void* stream) {
+    if (!te || !pool || !dtab || !dpool_part || !dte_part || G <= 0 || C <= 0) return -1;
+    if (d < 1 || d > 16) return -2;
+    using namespace gptst::sm;
+    const size_t smem = ((size_t)TR * LDT + TR * LDE + 4 * 16 * 17) * 4;
+    cudaError_t e = cudaFuncSetAttribute(table_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((G + TR - 1) / TR, (C + TC - 1) / TC);
+    table_bwd_fused_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(te, pool, dtab, dpool_part, dte_part, G, d, C);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-node T x T mix matrix of hyperTem (GPTST.py:156-158):  M_n = A_n^T A_n,  A_n (Ht x T).  The batched 8x12 / 12x12
+// products were 30 us cuBLAS launches each way; here: one thread per output element.
+//     fwd: M[n][t][s] = sum_h A[n][h][t] A[n][h][s]          bwd: dA[n][h][t] = sum_s A[n][h][s] (dM[n][t][s] + dM[n][s][t])
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+__global__ void __launch_bounds__(256) mn_fwd_kernel(const float* __restrict__ A, float* __restrict__ M, int N, int Ht, int T) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N * T * T) return;
+    const int n = i / (T * T), t = (i / T) % T, s = i % T;
+    const float* a = A + (size_t)n * Ht * T;
+    float acc = 0.f;
+    for (int h = 0; h < Ht; ++h) acc = fmaf(a[h * T + t], a[h * T + s], acc);
+    M[i] = acc;
+}
+__global__ void __launch_bounds__(256) mn_bwd_kernel(const float* __restrict__ A, const float* __restrict__ dM, float* __restrict__ dA,
+                                                     int N, int Ht, int T) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N * Ht * T) return;
+    const int n = i / (Ht * T), h = (i / T) % Ht, t = i % T;
+    const float* a = A + ((size_t)n * Ht + h) * T;
+    const float* m = dM + (size_t)n * T * T;
+    float acc = 0.f;
+    for (int s = 0; s < T; ++s) acc = fmaf(a[s], m[t * T + s] + m[s * T + t], acc);
+    dA[i] = acc;
+}
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_mn_fwd(const float* A, float* M, int N, int Ht, int T, void* stream) {
+    if (!A || !M || N <= 0 || Ht <= 0 || T <= 0) return -1;
+    gptst::sm::mn_fwd_kernel<<<(N * T * T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, M, N, Ht, T);
+    return (int)cudaGetLastError();
+}
+extern "C" int gptst_mn_bwd(const float* A, const float* dM, float* dA, int N, int Ht, int T, void* stream) {
+    if (!A || !dM || !dA || N <= 0 || Ht <= 0 || T <= 0) return -1;
+    gptst::sm::mn_bwd_kernel<<<(N * Ht * T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, dM, dA, N, Ht, T);
+    return (int)cudaGetLastError();
+}

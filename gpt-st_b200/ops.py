@@ -340,13 +340,49 @@ class _LowRankTable(torch.autograd.Function):
         _chk(te, pool, dtab)
         G, d = te.shape
         C = pool.shape[1]
+        L = _lib.lib()
+        st = _stream()
+        if G * C >= 65536:
+            # big tables: one fused tensor-core pass over dTab, partials per 64-row / 128-column chunk
+            rc, cc = (G + 63) // 64, (C + 127) // 128
+            dpool_part = torch.empty((rc, 16, C), device=te.device, dtype=torch.float32)
+            dte_part = torch.empty((cc, G, 16), device=te.device, dtype=torch.float32)
+            _lib.check(L.gptst_table_bwd2(_p(te), _p(pool), _p(dtab), _p(dpool_part), _p(dte_part), G, d, C, st), "gptst_table_bwd2")
+            dpool = (dpool_part[0] if rc == 1 else dpool_part.sum(0))[:d]
+            dte = (dte_part[0] if cc == 1 else dte_part.sum(0))[:, :d]
+            return dte, dpool
         dpool = torch.empty_like(pool) if ctx.needs_input_grad[1] else None
         dte = torch.empty_like(te) if ctx.needs_input_grad[0] else None
-        st = _stream()
         if dpool is not None and dte is not None:
             _count(1)
-        _lib.check(_lib.lib().gptst_table_bwd(_p(te), _p(pool), _p(dtab), _p(dpool), _p(dte), G, d, C, st), "gptst_table_bwd")
+        _lib.check(L.gptst_table_bwd(_p(te), _p(pool), _p(dtab), _p(dpool), _p(dte), G, d, C, st), "gptst_table_bwd")
         return dte, dpool
+
+
+class _MixMatrix(torch.autograd.Function):
+    """M_n = A_n^T A_n for A (N, Ht, T) (hyperTem's two hops without a nonlinearity in between, GPTST.py:157-158)."""
+
+    @staticmethod
+    def forward(ctx, A):
+        A = A.contiguous()
+        _chk(A)
+        N, Ht, T = A.shape
+        M = torch.empty((N, T, T), device=A.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gptst_mn_fwd(_p(A), _p(M), N, Ht, T, _stream()), "gptst_mn_fwd")
+        ctx.save_for_backward(A)
+        return M
+
+    @staticmethod
+    def backward(ctx, dM):
+        (A,) = ctx.saved_tensors
+        N, Ht, T = A.shape
+        dA = torch.empty_like(A)
+        _lib.check(_lib.lib().gptst_mn_bwd(_p(A), _p(dM.contiguous()), _p(dA), N, Ht, T, _stream()), "gptst_mn_bwd")
+        return dA
+
+
+def mix_matrix(A):
+    return _MixMatrix.apply(A)
 
 
 def lowrank_table(te, pool):

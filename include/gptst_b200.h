@@ -144,6 +144,14 @@ int gptst_time_mlp_bwd(const float* a, const float* b, const float* W1, const fl
  * dpool[k][c] = sum_g te[g][k] dTab[g][c], dte[g][k] = sum_c dTab[g][c] pool[k][c]; either output may be NULL.          */
 int gptst_table_bwd(const float* te, const float* pool, const float* dtab, float* dpool, float* dte, int G, int d, int C,
                     void* stream);
+/* the same, fused on the tensor cores (dTab read once): dpool_part (row_chunks, 16, C), dte_part (col_chunks, G, 16), chunk
+ * counts from gptst_table_bwd2_chunks; the caller sums the partials and drops the rows / columns >= d.                     */
+int gptst_table_bwd2_chunks(int G, int C, int* row_chunks, int* col_chunks);
+int gptst_table_bwd2(const float* te, const float* pool, const float* dtab, float* dpool_part, float* dte_part, int G, int d,
+                     int C, void* stream);
+/* per-node mix matrix of hyperTem, GPTST.py:156-158: M[n] = A[n]^T A[n] (A (N,Ht,T)) and its backward dA = A (dM + dM^T)   */
+int gptst_mn_fwd(const float* A, float* M, int N, int Ht, int T, void* stream);
+int gptst_mn_bwd(const float* A, const float* dM, float* dA, int N, int Ht, int T, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
 

@@ -397,7 +397,8 @@ def test_affine1_matches_linear():
     check(b.grad, lin.bias.grad, 5e-6, "affine1 db")
 
 
-@pytest.mark.parametrize("G,d,C", [(768, 16, 4096), (170, 16, 64), (36, 4, 1700), (5, 4, 1920), (7, 16, 100)])
+@pytest.mark.parametrize("G,d,C", [(768, 16, 4096), (170, 16, 4096), (768, 4, 1700), (64, 4, 1920), (100, 16, 1001), (170, 16, 64),
+                                   (36, 4, 1700), (5, 4, 1920), (7, 16, 100)])
 def test_lowrank_table_backward(G, d, C):
     from gptst_b200 import ops
     te, pool, g = rnd(G, d, seed=1).requires_grad_(), rnd(d, C, seed=2).requires_grad_(), rnd(G, C, seed=3)
