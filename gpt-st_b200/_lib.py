@@ -47,6 +47,7 @@ SIGNATURES = {
     "gptst_time_mlp_grad_floats": (_i, [_i, _i]),
     "gptst_time_mlp_fwd": (_i, [_f] * 16 + [_i, _i, _i, _l, _f]),
     "gptst_time_mlp_bwd": (_i, [_f] * 10 + [_i, _i, _i, _l, _f]),
+    "gptst_table_fwd": (_i, [_f, _f, _f, _i, _i, _i, _f]),
     "gptst_table_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f]),
     "gptst_table_bwd2_chunks": (_i, [_i, _i, _f, _f]),
     "gptst_table_bwd2": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _f]),

@@ -523,3 +523,56 @@ extern "C" int gptst_mn_bwd(const float* A, const float* dM, float* dA, int N, i
     gptst::sm::mn_bwd_kernel<<<(N * Ht * T + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, dM, dA, N, Ht, T);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forward of a low-rank table  Tab[g][c] = sum_k te[g][k] pool[k][c]  as a streaming kernel: a thread keeps the d x 4
+// pool block of its four columns in registers and walks 16 rows (te rows broadcast from shared memory); the output
+// (12.6 MB for the time-adaptive weights) is written with 16-byte stores.  cuBLAS needs ~30 us for this K = 16 product.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+constexpr int kTabRows = 16;
+__global__ void __launch_bounds__(256) table_fwd_kernel(const float* __restrict__ te, const float* __restrict__ pool,
+                                                        float* __restrict__ tab, int G, int d, int C) {
+    __shared__ float tes[kTabRows][kDmax];
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.y * kTabRows;
+    {
+        const int r = tid / kDmax, k = tid % kDmax;       // 256 threads = 16 rows x 16
+        tes[r][k] = (r0 + r < G && k < d) ? te[(size_t)(r0 + r) * d + k] : 0.f;
+    }
+    __syncthreads();
+    const int c = (blockIdx.x * 256 + tid) * 4;
+    if (c >= C) return;
+    const bool vec = (C % 4 == 0) && (c + 3 < C);
+    float4 p[kDmax];
+#pragma unroll
+    for (int k = 0; k < kDmax; ++k) {
+        if (k < d) {
+            if (vec) p[k] = *reinterpret_cast<const float4*>(pool + (size_t)k * C + c);
+            else p[k] = make_float4(pool[(size_t)k * C + c], c + 1 < C ? pool[(size_t)k * C + c + 1] : 0.f,
+                                    c + 2 < C ? pool[(size_t)k * C + c + 2] : 0.f, c + 3 < C ? pool[(size_t)k * C + c + 3] : 0.f);
+        } else p[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int r = 0; r < kTabRows && r0 + r < G; ++r) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kDmax; ++k) {
+            const float t = tes[r][k];
+            o.x = fmaf(t, p[k].x, o.x); o.y = fmaf(t, p[k].y, o.y); o.z = fmaf(t, p[k].z, o.z); o.w = fmaf(t, p[k].w, o.w);
+        }
+        float* dst = tab + (size_t)(r0 + r) * C + c;
+        if (vec) *reinterpret_cast<float4*>(dst) = o;
+        else { dst[0] = o.x; if (c + 1 < C) dst[1] = o.y; if (c + 2 < C) dst[2] = o.z; if (c + 3 < C) dst[3] = o.w; }
+    }
+}
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_table_fwd(const float* te, const float* pool, float* tab, int G, int d, int C, void* stream) {
+    if (!te || !pool || !tab || G <= 0 || C <= 0) return -1;
+    if (d < 1 || d > gptst::sm::kDmax) return -2;
+    dim3 grid((C + 1023) / 1024, (G + gptst::sm::kTabRows - 1) / gptst::sm::kTabRows);
+    gptst::sm::table_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(te, pool, tab, G, d, C);
+    return (int)cudaGetLastError();
+}

@@ -325,13 +325,19 @@ def time_mlp(ab, mod):
 
 class _LowRankTable(torch.autograd.Function):
     """Tab = te . pool with te (G, d), pool (d, C), d <= 16: the generators of every adaptive table of the model.  Forward is
-    a plain matmul (off the critical path, on the prologue streams); the backward pair of skinny products runs as two
-    streaming kernels instead of cuBLAS SIMT split-K GEMMs."""
+    a streaming kernel (the K = 16 product is write-bound); the backward pair of skinny products runs fused on the tensor
+    cores (big tables) or as two streaming kernels, instead of cuBLAS SIMT split-K GEMMs."""
 
     @staticmethod
     def forward(ctx, te, pool):
+        te, pool = te.contiguous(), pool.contiguous()
+        _chk(te, pool)
         ctx.save_for_backward(te, pool)
-        return te @ pool
+        G, d = te.shape
+        C = pool.shape[1]
+        tab = torch.empty((G, C), device=te.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gptst_table_fwd(_p(te), _p(pool), _p(tab), G, d, C, _stream()), "gptst_table_fwd")
+        return tab
 
     @staticmethod
     def backward(ctx, dtab):

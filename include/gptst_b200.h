@@ -140,6 +140,8 @@ int gptst_time_mlp_fwd(const float* a, const float* b, const float* Wd, const fl
 int gptst_time_mlp_bwd(const float* a, const float* b, const float* W1, const float* W2, const float* W3, const float* h0,
                        const float* z1, const float* z2, const float* g, float* part, int R, int F, int e, long in_stride,
                        void* stream);
+/* forward of a low-rank table: tab (G,C) = te (G,d) . pool (d,C), d <= 16 */
+int gptst_table_fwd(const float* te, const float* pool, float* tab, int G, int d, int C, void* stream);
 /* backward of a low-rank table Tab = te . pool (te (G,d), pool (d,C), d <= 16; GPTST.py:104, :129, :137-138, :160-161, :24-31):
  * dpool[k][c] = sum_g te[g][k] dTab[g][c], dte[g][k] = sum_c dTab[g][c] pool[k][c]; either output may be NULL.          */
 int gptst_table_bwd(const float* te, const float* pool, const float* dtab, float* dpool, float* dte, int G, int d, int C,
