@@ -32,6 +32,8 @@ SIGNATURES = {
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd_parts": (_i, [_i]),
     "gptst_cap_hop_bwd2": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_dv_dcr_hoprows": (_i, [_f] * 9 + [_i] * 6 + [_f]),
+    "gptst_cap_hop_bwd_cols": (_i, [_f] * 7 + [_i] * 5 + [_f]),
     "gptst_cap_route_bwd_parts": (_i, [_i, _i, _i, _i, _i]),
     "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route2_supported": (_i, [_i, _i, _i]),

@@ -56,9 +56,11 @@ __global__ void __launch_bounds__(256) cap_recon_hop_kernel(const float* __restr
     float* E1 = smem;                      // [HT][D]
     float* dy = E1 + (size_t)HT * D;       // [HT][H]   dyn[b][:, t*H .. t*H+H)
     float* vs = dy + (size_t)HT * H;       // [H][D]
+    float* cs = vs + (size_t)H * D;        // [H][N]  the slab's incidence (staged up front: its latency hides under the hop)
     const int slab = blockIdx.x, b = slab / T, tt = slab % T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = T * H;
+    for (int i = tid; i < H * N; i += 256) cs[i] = c[(size_t)slab * H * N + i];
     for (int i = tid; i < HT * D / 4; i += 256)
         reinterpret_cast<float4*>(E1)[i] = reinterpret_cast<const float4*>(e1 + (size_t)b * HT * D)[i];
     for (int i = tid; i < HT * H; i += 256) dy[i] = dyn[((size_t)b * HT + i / H) * K + tt * H + (i % H)];
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(256) cap_recon_hop_kernel(const float* __restr
     for (int n = blockIdx.y * NPC + nl; n < N; n += gridDim.y * NPC) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int h = 0; h < H; ++h) {
-            const float cc = c[((size_t)slab * H + h) * N + n];
+            const float cc = cs[h * N + n];
             const float4 vv = *reinterpret_cast<const float4*>(vs + h * D + cv * 4);
             o.x = fmaf(cc, vv.x, o.x); o.y = fmaf(cc, vv.y, o.y); o.z = fmaf(cc, vv.z, o.z); o.w = fmaf(cc, vv.w, o.w);
         }
@@ -234,12 +236,19 @@ extern "C" int gptst_cap_recon_hop(const float* c, const float* s, const float* 
     int want = (592 + B * T - 1) / (B * T);
     if (ychunks > want) ychunks = want;
     if (ychunks < 1) ychunks = 1;
-    const size_t smem = ((size_t)HT * D + (size_t)HT * H + (size_t)H * D) * 4;
-    if (smem > 48 * 1024) return -2;
+    const size_t smem = ((size_t)HT * D + (size_t)HT * H + (size_t)H * D + (size_t)H * N) * 4;
+    if (smem > kSmemMax) return -2;
     dim3 grid(B * T, ychunks);
-    if (D == 64) cap_recon_hop_kernel<64><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
-    else if (D == 128) cap_recon_hop_kernel<128><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
-    else return -2;
+    cudaError_t e;
+    if (D == 64) {
+        e = cudaFuncSetAttribute(cap_recon_hop_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        cap_recon_hop_kernel<64><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
+    } else if (D == 128) {
+        e = cudaFuncSetAttribute(cap_recon_hop_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        cap_recon_hop_kernel<128><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
+    } else return -2;
     return (int)cudaGetLastError();
 }
 
@@ -264,5 +273,20 @@ extern "C" int gptst_cap_hop_bwd2(const float* s, const float* dyn, const float*
     e = cudaFuncSetAttribute(cap_hop_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return (int)e;
     cap_hop_bwd_cols_kernel<<<dim3(B, D / kE1Cols), 256, smem2, st>>>(s, dyn, e1, dr_tmp, dpre2_tmp, ds, ddyn_part, B, T, D, H, HT);
+    return (int)cudaGetLastError();
+}
+
+// column pass only (dr / dpre2 already produced, e.g. by gptst_cap_dv_dcr_hoprows)
+extern "C" int gptst_cap_hop_bwd_cols(const float* s, const float* dyn, const float* e1, const float* dr, const float* dpre2,
+                                      float* ds, float* ddyn_part, int B, int T, int D, int H, int HT, void* stream) {
+    if (!s || !dyn || !e1 || !dr || !dpre2 || !ds || !ddyn_part || B <= 0 || T <= 0 || HT <= 0) return -1;
+    if (H < 1 || H > kMaxH || D % kE1Cols != 0) return -2;
+    const int K = T * H;
+    const size_t smem2 = ((size_t)2 * K * kE1Cols + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
+    if (smem2 > kSmemMax) return -2;
+    cudaError_t e = cudaFuncSetAttribute(cap_hop_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    cap_hop_bwd_cols_kernel<<<dim3(B, D / kE1Cols), 256, smem2, (cudaStream_t)stream>>>(s, dyn, e1, dr, dpre2, ds, ddyn_part, B, T, D,
+                                                                                      H, HT);
     return (int)cudaGetLastError();
 }

@@ -211,14 +211,22 @@ class _CapCore(torch.autograd.Function):
         _count(3)  # dv_dcr + hop_bwd2 (two launches) + route_bwd share `st`
         dout = dout.contiguous()
         drecon, dWn, dbn, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True)
-        dv = torch.empty_like(s)
         dcr = torch.empty_like(c)
-        _lib.check(L.gptst_cap_dv_dcr(_p(c), _p(v), _p(drecon), _p(dv), _p(dcr), B, T, N, D, H, st), "gptst_cap_dv_dcr")
         ds = torch.empty_like(s)
         dr_tmp, dp2_tmp = torch.empty_like(s), torch.empty_like(s)
         ddyn_part = torch.empty((L.gptst_cap_hop_bwd_parts(D),) + tuple(dyn.shape), device=x.device, dtype=torch.float32)
-        _lib.check(L.gptst_cap_hop_bwd2(_p(s), _p(dyn), _p(e1), _p(dv), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D,
-                                        H, HT, st), "gptst_cap_hop_bwd2")
+        if L.gptst_cap_route2_supported(N, D, H):
+            # dv/dcr with the row pass of the hop backward in its tail, then the column pass
+            _count(-1)
+            _lib.check(L.gptst_cap_dv_dcr_hoprows(_p(c), _p(v), _p(drecon), _p(s), _p(dyn), _p(e1), _p(dcr), _p(dr_tmp), _p(dp2_tmp), B, T,
+                                                  N, D, H, HT, st), "gptst_cap_dv_dcr_hoprows")
+            _lib.check(L.gptst_cap_hop_bwd_cols(_p(s), _p(dyn), _p(e1), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D, H, HT,
+                                                st), "gptst_cap_hop_bwd_cols")
+        else:
+            dv = torch.empty_like(s)
+            _lib.check(L.gptst_cap_dv_dcr(_p(c), _p(v), _p(drecon), _p(dv), _p(dcr), B, T, N, D, H, st), "gptst_cap_dv_dcr")
+            _lib.check(L.gptst_cap_hop_bwd2(_p(s), _p(dyn), _p(e1), _p(dv), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D,
+                                            H, HT, st), "gptst_cap_hop_bwd2")
         ddyn = ddyn_part.sum(0)
         ddadj = torch.empty_like(c)
         if L.gptst_cap_route2_supported(N, D, H):

@@ -85,6 +85,13 @@ int gptst_cap_hop_bwd(const float* s, const float* dyn, const float* dv, float* 
 int gptst_cap_hop_bwd_parts(int D);
 int gptst_cap_hop_bwd2(const float* s, const float* dyn, const float* e1, const float* dv, float* dr_tmp, float* dpre2_tmp,
                        float* ds, float* ddyn_part, int B, int T, int D, int H, int HT, void* stream);
+/* dv/dcr fused with the row pass of the hop backward (D = 64, N <= 256): writes dcr and, instead of dv, dr = squash'(r, dv) and
+ * dpre2 = dr * phi'(pre2); gptst_cap_hop_bwd_cols is the remaining column pass (-> ds, ddyn_part).                       */
+int gptst_cap_dv_dcr_hoprows(const float* c, const float* v, const float* drecon, const float* s, const float* dyn,
+                             const float* e1, float* dcr, float* dr, float* dpre2, int B, int T, int N, int D, int H, int HT,
+                             void* stream);
+int gptst_cap_hop_bwd_cols(const float* s, const float* dyn, const float* e1, const float* dr, const float* dpre2, float* ds,
+                           float* ddyn_part, int B, int T, int D, int H, int HT, void* stream);
 /* dx_io holds dy = dOut*act'(out) on entry and dy + dZ Wp on exit; ddadj (B,T,H,N);
  * dWp_part (parts,D,D) [out][in], dbp_part (parts,D) with parts = gptst_cap_route_bwd_parts(...)              */
 int gptst_cap_route_bwd_parts(int B, int T, int N, int D, int H);
