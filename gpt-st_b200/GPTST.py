@@ -61,8 +61,9 @@ class MLP_RL(nn.Module):
     def tables_tem(self, time_eb):
         return ops.lowrank_table(time_eb, self.weights_pool_tem), ops.lowrank_table(time_eb, self.bias_pool_tem)
 
-    def forward(self, eb, time_eb, node_eb, tables=None):
-        """tables = ((Wn, bn, event), (Wt, bt, event)) when the caller produced them on side streams."""
+    def forward(self, eb, time_eb, node_eb, tables=None, probs=False):
+        """tables = ((Wn, bn, event), (Wt, bt, event)) when the caller produced them on side streams.  probs=True returns
+        softmax(logits) through the fused score head instead of the logits."""
         h0 = _affine(self.ln1, eb)                                                # (B,T,N,D)
         if tables is None:
             Wn, bn = self.tables_spa(node_eb)
@@ -75,6 +76,8 @@ class MLP_RL(nn.Module):
             h1 = ops.node_adaptive_proj(h0, Wn, bn)
             torch.cuda.current_stream().wait_event(ev_t)
             h2 = ops.time_adaptive_proj(h1, Wt, bt)
+        if probs:
+            return ops.score_head(h2, self.ln3.weight, self.ln3.bias)
         return self.ln3(h2)
 
 
@@ -300,6 +303,8 @@ class Hypergraph_encoder(nn.Module):
         i0 = self.input_base_dim
         if aux is None:
             time_eb = self.teb4mask(source[:, :, 0, i0:i0 + 2])
+            if source.is_cuda:
+                return self.MLP_RL(source[..., 0:i0], time_eb, self.neb4mask, None, True)
             logits = self.MLP_RL(source[..., 0:i0], time_eb, self.neb4mask)
             return F.softmax(logits, dim=-1)
         cur = torch.cuda.current_stream()
@@ -319,8 +324,7 @@ class Hypergraph_encoder(nn.Module):
             ev_n.record(sb)
         for t_ in (Wt, bt, Wn, bn):
             t_.record_stream(cur)
-        logits = self.MLP_RL(source[..., 0:i0], None, None, ((Wn, bn, ev_n), (Wt, bt, ev_t)))
-        return F.softmax(logits, dim=-1)
+        return self.MLP_RL(source[..., 0:i0], None, None, ((Wn, bn, ev_n), (Wt, bt, ev_t)), True)
 
     def _budgets(self, n_cells, epoch):
         tp = ((epoch - self.change_epoch) / (self.epochs - self.change_epoch)) * self.ada_mask_ratio

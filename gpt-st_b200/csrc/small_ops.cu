@@ -576,3 +576,78 @@ extern "C" int gptst_table_fwd(const float* te, const float* pool, float* tab, i
     gptst::sm::table_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(te, pool, tab, G, d, C);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Score head of the mask scorer (GPTST.py:33 ln3 + the caller's softmax, :332/:343): prob = softmax(h W3^T + b3) per cell.
+// It sits on the critical front of the adaptive phase (the encoder waits for the mask); as library calls it was a
+// 64 -> 10 GEMM + bias epilogue + softmax (48 us).  CTA = 256 rows staged with 16-byte row chunks, thread = row.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+template <int D>
+__global__ void __launch_bounds__(256) score_head_kernel(const float* __restrict__ h, const float* __restrict__ W3,
+                                                         const float* __restrict__ b3, float* __restrict__ prob, long rows, int H) {
+    constexpr int LDS = D + 1;
+    extern __shared__ __align__(16) float sh[];
+    float* tile = sh;                       // [256][D+1]
+    float* Ws = tile + 256 * LDS;           // [H][D]
+    float* bs = Ws + kMaxH * D;             // [H]
+    float* ps = bs + kMaxH;                 // [256][H] output staging
+    const int tid = threadIdx.x;
+    const long r0 = (long)blockIdx.x * 256;
+    for (int i = tid; i < H * D; i += 256) Ws[i] = W3[i];
+    if (tid < H) bs[tid] = b3[tid];
+    for (int i = tid; i < 256 * (D / 4); i += 256) {
+        const int r = i / (D / 4), q = i % (D / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < rows) v = *reinterpret_cast<const float4*>(h + (r0 + r) * D + 4 * q);
+        float* dst = tile + r * LDS + 4 * q;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    float z[kMaxH];
+#pragma unroll
+    for (int j = 0; j < kMaxH; ++j) z[j] = (j < H) ? bs[j] : -INFINITY;
+    const float* row = tile + tid * LDS;
+    for (int d = 0; d < D; ++d) {
+        const float x = row[d];
+#pragma unroll
+        for (int j = 0; j < kMaxH; ++j)
+            if (j < H) z[j] = fmaf(x, Ws[j * D + d], z[j]);
+    }
+    float m = z[0];
+#pragma unroll
+    for (int j = 1; j < kMaxH; ++j) m = fmaxf(m, z[j]);
+    float ssum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxH; ++j) { z[j] = (j < H) ? expf(z[j] - m) : 0.f; ssum += z[j]; }
+    const float inv = 1.f / ssum;
+#pragma unroll
+    for (int j = 0; j < kMaxH; ++j)
+        if (j < H) ps[tid * H + j] = z[j] * inv;
+    __syncthreads();
+    long nvalid = rows - r0;
+    if (nvalid > 256) nvalid = 256;
+    for (long i = tid; i < nvalid * H; i += 256) prob[r0 * H + i] = ps[i];
+}
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_score_head_fwd(const float* h, const float* W3, const float* b3, float* prob, long rows, int D, int H,
+                                    void* stream) {
+    if (!h || !W3 || !b3 || !prob || rows <= 0) return -1;
+    if (H < 1 || H > gptst::kMaxH || (D != 64 && D != 128)) return -2;
+    const size_t smem = ((size_t)256 * (D + 1) + (size_t)gptst::kMaxH * D + gptst::kMaxH + 256 * (size_t)H) * 4;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    cudaError_t e;
+    if (D == 64) {
+        e = cudaFuncSetAttribute(gptst::sm::score_head_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        gptst::sm::score_head_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(h, W3, b3, prob, rows, H);
+    } else {
+        e = cudaFuncSetAttribute(gptst::sm::score_head_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        gptst::sm::score_head_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(h, W3, b3, prob, rows, H);
+    }
+    return (int)cudaGetLastError();
+}

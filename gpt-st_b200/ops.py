@@ -408,6 +408,34 @@ def lowrank_table(te, pool):
     return out.view(te.shape[:-1] + pool.shape[1:])
 
 
+class _ScoreHead(torch.autograd.Function):
+    """prob = softmax(h W3^T + b3): forward in one kernel (critical front of the adaptive phase); the backward (KL branch, on the
+    scorer's side stream) uses the closed forms with library ops."""
+
+    @staticmethod
+    def forward(ctx, h, W3, b3):
+        h, W3, b3 = h.contiguous(), W3.contiguous(), b3.contiguous()
+        _chk(h, W3, b3)
+        D, H = h.shape[-1], W3.shape[0]
+        rows = h.numel() // D
+        prob = torch.empty(h.shape[:-1] + (H,), device=h.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gptst_score_head_fwd(_p(h), _p(W3), _p(b3), _p(prob), rows, D, H, _stream()), "gptst_score_head_fwd")
+        ctx.save_for_backward(h, W3, prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        h, W3, prob = ctx.saved_tensors
+        dz = prob * (dprob - (prob * dprob).sum(-1, keepdim=True))          # softmax backward
+        dz2 = dz.reshape(-1, dz.shape[-1])
+        dh = (dz2 @ W3).view_as(h) if ctx.needs_input_grad[0] else None
+        return dh, dz2.t() @ h.reshape(-1, h.shape[-1]), dz2.sum(0)
+
+
+def score_head(h, W3, b3):
+    return _ScoreHead.apply(h, W3, b3)
+
+
 class _Affine1(torch.autograd.Function):
     """y = x w + b for a linear layer with ONE input feature; the backward is a single pass over dy."""
 

@@ -409,3 +409,18 @@ def test_lowrank_table_backward(G, d, C):
     out.backward(g.float().cuda())
     check(tc.grad, te.grad, 5e-6, "table dte")
     check(pc.grad, pool.grad, 5e-6, "table dpool")
+
+
+def test_score_head_matches_torch():
+    from gptst_b200 import ops
+    h, W3, b3 = rnd(3, 12, 37, 64, seed=1).requires_grad_(), rnd(10, 64, seed=2, scale=0.2).requires_grad_(), rnd(10, seed=3).requires_grad_()
+    want = torch.softmax(h @ W3.t() + b3, -1)
+    g = rnd(3, 12, 37, 10, seed=4)
+    want.backward(g)
+    hc, Wc, bc = (t.detach().float().cuda().requires_grad_() for t in (h, W3, b3))
+    got = ops.score_head(hc, Wc, bc)
+    check(got, want.detach(), 2e-6, "score head prob")
+    got.backward(g.float().cuda())
+    check(hc.grad, h.grad, 1e-5, "score head dh")
+    check(Wc.grad, W3.grad, 1e-5, "score head dW3")
+    check(bc.grad, b3.grad, 1e-5, "score head db3")
