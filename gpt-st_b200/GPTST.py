@@ -496,7 +496,9 @@ class GPTST_Model(nn.Module):
         key = (dev.index, main.cuda_stream)
         if self._streams is None or self._streams[0] != key:
             self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(9)], [torch.cuda.Stream(device=dev) for _ in range(9)],
-                             torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev) for _ in range(2)])
+                             torch.cuda.Stream(device=dev, priority=-1), [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)])
+            # the scorer (and its two table streams) is on the critical front of the adaptive phase -- the encoder cannot start
+            # before the mask exists -- so it gets the priority of the main chain; the STHCN prologues keep the default (lowest)
         fork = torch.cuda.Event()
         fork.record(main)
         out = []

@@ -590,12 +590,12 @@ __global__ void __launch_bounds__(256) score_head_kernel(const float* __restrict
     constexpr int LDS = D + 1;
     extern __shared__ __align__(16) float sh[];
     float* tile = sh;                       // [256][D+1]
-    float* Ws = tile + 256 * LDS;           // [H][D]
+    float* Ws = tile + 256 * LDS + ((256 * LDS) % 4 ? 4 - (256 * LDS) % 4 : 0);   // [D][16] (transposed, 16-byte aligned)
     float* bs = Ws + kMaxH * D;             // [H]
     float* ps = bs + kMaxH;                 // [256][H] output staging
     const int tid = threadIdx.x;
     const long r0 = (long)blockIdx.x * 256;
-    for (int i = tid; i < H * D; i += 256) Ws[i] = W3[i];
+    for (int i = tid; i < kMaxH * D; i += 256) { const int d = i / kMaxH, j = i % kMaxH; Ws[i] = (j < H) ? W3[j * D + d] : 0.f; }
     if (tid < H) bs[tid] = b3[tid];
     for (int i = tid; i < 256 * (D / 4); i += 256) {
         const int r = i / (D / 4), q = i % (D / 4);
@@ -609,12 +609,22 @@ __global__ void __launch_bounds__(256) score_head_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < kMaxH; ++j) z[j] = (j < H) ? bs[j] : -INFINITY;
     const float* row = tile + tid * LDS;
+    // W3 is held transposed, [d][16]: four 16-byte broadcast loads per column instead of one 4-byte load per (column, class)
+#pragma unroll 4
     for (int d = 0; d < D; ++d) {
         const float x = row[d];
+        const float4* w4 = reinterpret_cast<const float4*>(Ws + d * kMaxH);
 #pragma unroll
-        for (int j = 0; j < kMaxH; ++j)
-            if (j < H) z[j] = fmaf(x, Ws[j * D + d], z[j]);
+        for (int q = 0; q < kMaxH / 4; ++q) {
+            if (4 * q < H) {
+                const float4 w = w4[q];
+                z[4 * q] = fmaf(x, w.x, z[4 * q]); z[4 * q + 1] = fmaf(x, w.y, z[4 * q + 1]);
+                z[4 * q + 2] = fmaf(x, w.z, z[4 * q + 2]); z[4 * q + 3] = fmaf(x, w.w, z[4 * q + 3]);
+            }
+        }
     }
+#pragma unroll
+    for (int j = 0; j < kMaxH; ++j) if (j >= H) z[j] = -INFINITY;
     float m = z[0];
 #pragma unroll
     for (int j = 1; j < kMaxH; ++j) m = fmaxf(m, z[j]);
@@ -649,5 +659,33 @@ extern "C" int gptst_score_head_fwd(const float* h, const float* W3, const float
         if (e != cudaSuccess) return (int)e;
         gptst::sm::score_head_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(h, W3, b3, prob, rows, H);
     }
+    return (int)cudaGetLastError();
+}
+
+// y[i][:] = x[i] * w[:] + b[:]   (a linear layer with one input feature, GPTST.py:22 / :298) -- a write-bound streaming kernel
+namespace gptst {
+namespace sm {
+__global__ void __launch_bounds__(256) affine1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ y, long n, int D) {
+    const int q4 = D / 4;
+    const long total = n * q4;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const long r = i / q4;
+        const int q = (int)(i % q4);
+        const float xv = x[r];
+        const float4 wv = *reinterpret_cast<const float4*>(w + 4 * q), bv = *reinterpret_cast<const float4*>(b + 4 * q);
+        *reinterpret_cast<float4*>(y + r * D + 4 * q) =
+            make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w));
+    }
+}
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream) {
+    if (!x || !w || !b || !y || n <= 0) return -1;
+    if (D < 4 || D % 4 != 0) return -2;
+    long blocks = (n * (D / 4) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gptst::sm::affine1_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, b, y, n, D);
     return (int)cudaGetLastError();
 }
