@@ -425,13 +425,20 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
 // ------------------------------------------------------------------------------------------------------------------
 // launch policy
 // ------------------------------------------------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 static int pick_nw(int R) {   // warps (= 16-row tiles) per CTA chunk
+    static const int mid = env_int("GPTST_B200_GP2_MID", 11);    // 129..176 rows: 11 (one chunk) or 6 (two chunks, 3 CTAs/SM)
+    static const int lng = env_int("GPTST_B200_GP2_LONG", 8);    // long groups: chunks of 128 rows (8) or 64 rows (4)
     if (R <= 64) return 4;
+    if (R <= 96) return 6;
     if (R <= 128) return 8;
-    if (R <= 176) return 11;
+    if (R <= 176) return mid == 6 ? 6 : 11;
     if (R <= 208) return 13;
     if (R <= 256) return 16;
-    return 8;                  // long groups (node-grouped: R = B*T): chunks of 128 rows
+    return lng == 4 ? 4 : (lng == 16 ? 16 : 8);   // long groups (node-grouped: R = B*T)
 }
 
 template <int NW, int MINB, int PREC>
@@ -462,6 +469,7 @@ static cudaError_t launch_bwd(const float* dY, const float* Y, const float* X, c
 #define GP2_DISPATCH(FN, ...)                                         \
     switch (pick_nw(R)) {                                             \
         case 4: return FN<4, 4, PREC>(__VA_ARGS__);                   \
+        case 6: return FN<6, 3, PREC>(__VA_ARGS__);                   \
         case 8: return FN<8, 2, PREC>(__VA_ARGS__);                   \
         case 11: return FN<11, 2, PREC>(__VA_ARGS__);                 \
         case 13: return FN<13, 1, PREC>(__VA_ARGS__);                 \

@@ -689,3 +689,64 @@ extern "C" int gptst_affine1_fwd(const float* x, const float* w, const float* b,
     gptst::sm::affine1_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, w, b, y, n, D);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sum of per-CTA / per-split gradient partials for up to 8 tensors in ONE launch:  out_s[i] = sum_p in_s[p * numel_s + i]
+// (fixed order -> deterministic).  A cap backward ends with five such reductions (dW_n, db_n, ddyn, dWp, dbp); as separate
+// library reductions they cost ~7 us each on the main chain.
+// ------------------------------------------------------------------------------------------------------------------
+namespace gptst {
+namespace sm {
+struct SumSegs {
+    const float* in[8];
+    float* out[8];
+    long numel[8];
+    int parts[8];
+    long start[9];     // prefix sums of numel (in float4 units where possible is not assumed: scalar elements)
+    int n;
+};
+__global__ void __launch_bounds__(256) sum_partials_kernel(SumSegs s) {
+    const long total = s.start[s.n];
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) k += (j < s.n && i >= s.start[j]);
+        const long e = i - s.start[k];
+        const float* p = s.in[k] + e;
+        const long stride = s.numel[k];
+        const int parts = s.parts[k];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int q = 0;
+        for (; q + 3 < parts; q += 4) {
+            a0 += p[(long)q * stride]; a1 += p[(long)(q + 1) * stride]; a2 += p[(long)(q + 2) * stride]; a3 += p[(long)(q + 3) * stride];
+        }
+        for (; q < parts; ++q) a0 += p[(long)q * stride];
+        s.out[k][e] = (a0 + a1) + (a2 + a3);
+    }
+}
+}  // namespace sm
+}  // namespace gptst
+
+// ins[k]: (parts[k], numel[k]) contiguous partials, outs[k]: (numel[k]); n <= 8 segments
+extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n,
+                                  void* stream) {
+    if (!ins || !outs || !numel || !parts || n <= 0) return -1;
+    if (n > 8) return -2;
+    gptst::sm::SumSegs s;
+    long tot = 0;
+    for (int k = 0; k < 8; ++k) {
+        s.start[k] = tot;
+        if (k < n) {
+            if (!ins[k] || !outs[k] || numel[k] <= 0 || parts[k] <= 0) return -1;
+            s.in[k] = ins[k]; s.out[k] = outs[k]; s.numel[k] = numel[k]; s.parts[k] = parts[k];
+            tot += numel[k];
+        } else { s.in[k] = nullptr; s.out[k] = nullptr; s.numel[k] = 0; s.parts[k] = 0; }
+    }
+    s.start[8] = tot;
+    for (int k = n; k < 9; ++k) s.start[k] = tot;
+    s.n = n;
+    long blocks = (tot + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    gptst::sm::sum_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+    return (int)cudaGetLastError();
+}

@@ -67,6 +67,25 @@ def _p(t):
 # ---------------------------------------------------------------------------------------------------
 # thin kernel wrappers (no autograd)
 # ---------------------------------------------------------------------------------------------------
+def sum_partials(*parts):
+    """Each argument is a (P, ...) tensor of per-CTA / per-split partials; returns the tuple of sums over dim 0, all computed by
+    ONE launch (fixed order, deterministic).  Tensors with P == 1 are returned as views."""
+    import ctypes as C
+    todo = [(i, t.contiguous()) for i, t in enumerate(parts) if t.shape[0] > 1]
+    outs = [t[0] if t.shape[0] == 1 else None for t in parts]
+    for k0 in range(0, len(todo), 8):
+        grp = todo[k0:k0 + 8]
+        res = [torch.empty(t.shape[1:], device=t.device, dtype=torch.float32) for _, t in grp]
+        n = len(grp)
+        ins = (C.c_void_p * n)(*[t.data_ptr() for _, t in grp])
+        ous = (C.c_void_p * n)(*[r.data_ptr() for r in res])
+        numel = (C.c_long * n)(*[r.numel() for r in res])
+        cnt = (C.c_int * n)(*[t.shape[0] for _, t in grp])
+        _lib.check(_lib.lib().gptst_sum_partials(C.cast(ins, C.c_void_p), C.cast(ous, C.c_void_p), C.cast(numel, C.c_void_p),
+                                                 C.cast(cnt, C.c_void_p), n, _stream()), "gptst_sum_partials")
+        for (i, _), r in zip(grp, res):
+            outs[i] = r
+    return tuple(outs)
 def gproj_fwd(X, W, bias, res, *, node_grouped: bool, act: bool, prec: int):
     """X (B,T,N,D).  time-grouped: W (B*T,D,D)/(B,T,D,D); node-grouped: W (N,D,D)."""
     B, T, N, D = X.shape
@@ -82,7 +101,7 @@ def gproj_fwd(X, W, bias, res, *, node_grouped: bool, act: bool, prec: int):
     return Y
 
 
-def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dres: bool):
+def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dres: bool, sum_parts: bool = True):
     B, T, N, D = X.shape
     dY, Y, X, W = _c(dY), _c(Y), _c(X), _c(W)
     _chk(dY, X, W)
@@ -99,8 +118,9 @@ def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dre
     rc = L.gptst_gproj_bwd(_p(dY), _p(Y) if act else None, _p(X), _p(W), _p(dX), _p(dWp), _p(dbp), _p(dres), G, R, gs, rs,
                            D, int(act), prec, splits, _stream())
     _lib.check(rc, "gptst_gproj_bwd")
-    dW = dWp[0] if splits == 1 else dWp.sum(0)
-    db = dbp[0] if splits == 1 else dbp.sum(0)
+    if not sum_parts:
+        return dX, dWp, dbp, dres          # raw (splits, ...) partials: the caller sums them together with others
+    dW, db = sum_partials(dWp, dbp)
     return dX, dW, db, dres
 
 
@@ -210,7 +230,8 @@ class _CapCore(torch.autograd.Function):
         st = _stream()
         _count(3)  # dv_dcr + hop_bwd2 (two launches) + route_bwd share `st`
         dout = dout.contiguous()
-        drecon, dWn, dbn, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True)
+        drecon, dWn_part, dbn_part, dx = gproj_bwd(dout, out, recon, Wn, node_grouped=True, act=True, prec=ctx.prec, want_dres=True,
+                                                   sum_parts=False)
         dcr = torch.empty_like(c)
         ds = torch.empty_like(s)
         dr_tmp, dp2_tmp = torch.empty_like(s), torch.empty_like(s)
@@ -227,7 +248,6 @@ class _CapCore(torch.autograd.Function):
             _lib.check(L.gptst_cap_dv_dcr(_p(c), _p(v), _p(drecon), _p(dv), _p(dcr), B, T, N, D, H, st), "gptst_cap_dv_dcr")
             _lib.check(L.gptst_cap_hop_bwd2(_p(s), _p(dyn), _p(e1), _p(dv), _p(dr_tmp), _p(dp2_tmp), _p(ds), _p(ddyn_part), B, T, D,
                                             H, HT, st), "gptst_cap_hop_bwd2")
-        ddyn = ddyn_part.sum(0)
         ddadj = torch.empty_like(c)
         if L.gptst_cap_route2_supported(N, D, H):
             # second generation: dZ per slab, then the shared-weight contractions as one linear-layer backward
@@ -247,7 +267,9 @@ class _CapCore(torch.autograd.Function):
             dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
             _lib.check(L.gptst_cap_route_bwd(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dx), _p(ddadj), _p(dWp_part),
                                              _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
-        return dx, dWp_part.sum(0), dbp_part.sum(0), ddadj, ddyn, dWn, dbn, None, None
+        # the five partial buffers of this backward are summed by one launch
+        dWn, dbn, ddyn, dWp, dbp = sum_partials(dWn_part, dbn_part, ddyn_part, dWp_part, dbp_part)
+        return dx, dWp, dbp, ddadj, ddyn, dWn, dbn, None, None
 
 
 def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None):
@@ -362,8 +384,8 @@ class _LowRankTable(torch.autograd.Function):
             dpool_part = torch.empty((rc, 16, C), device=te.device, dtype=torch.float32)
             dte_part = torch.empty((cc, G, 16), device=te.device, dtype=torch.float32)
             _lib.check(L.gptst_table_bwd2(_p(te), _p(pool), _p(dtab), _p(dpool_part), _p(dte_part), G, d, C, st), "gptst_table_bwd2")
-            dpool = (dpool_part[0] if rc == 1 else dpool_part.sum(0))[:d]
-            dte = (dte_part[0] if cc == 1 else dte_part.sum(0))[:, :d]
+            dpool, dte = sum_partials(dpool_part, dte_part)
+            dpool, dte = dpool[:d], dte[:, :d]
             return dte, dpool
         dpool = torch.empty_like(pool) if ctx.needs_input_grad[1] else None
         dte = torch.empty_like(te) if ctx.needs_input_grad[0] else None

@@ -163,6 +163,9 @@ int gptst_mn_fwd(const float* A, float* M, int N, int Ht, int T, void* stream);
 int gptst_mn_bwd(const float* A, const float* dM, float* dA, int N, int Ht, int T, void* stream);
 /* score head of the mask scorer (GPTST.py:33 + softmax of :332/:343): prob (rows,H) = softmax(h (rows,D) W3^T + b3), W3 (H,D)  */
 int gptst_score_head_fwd(const float* h, const float* W3, const float* b3, float* prob, long rows, int D, int H, void* stream);
+/* sums the (parts[k], numel[k]) partial buffers of up to 8 tensors in one launch, fixed order: outs[k][i] = sum_p ins[k][p][i]
+ * (host arrays of device pointers / sizes; the values are copied into the launch arguments)                                */
+int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n, void* stream);
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
