@@ -56,6 +56,8 @@ SIGNATURES = {
     "gptst_mn_fwd": (_i, [_f, _f, _i, _i, _i, _f]),
     "gptst_mn_bwd": (_i, [_f, _f, _f, _i, _i, _i, _f]),
     "gptst_score_head_fwd": (_i, [_f, _f, _f, _f, _l, _i, _i, _f]),
+    "gptst_score_head_bwd_parts": (_i, [_l]),
+    "gptst_score_head_bwd": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _i, _f]),
     "gptst_sum_partials": (_i, [_f, _f, _f, _f, _i, _f]),
     "gptst_affine1_fwd": (_i, [_f, _f, _f, _f, _l, _i, _f]),
     "gptst_affine1_bwd_parts": (_i, [_l]),

@@ -67,10 +67,20 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restri
 __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict__ part, int nparts, float* __restrict__ d_o,
                                                          long n, float kl_w, float* __restrict__ out) {
     __shared__ float tot[3];
-    if (threadIdx.x < 3) {
-        float s = 0.f;
-        for (int i = 0; i < nparts; ++i) s += part[i * 3 + threadIdx.x];   // fixed order: deterministic
-        tot[threadIdx.x] = s;
+    __shared__ float red[3][8];
+    {   // every block sums the partials itself, in a fixed (thread-strided, then tree) order: deterministic
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int i = threadIdx.x; i < nparts; i += 256) { s0 += part[i * 3]; s1 += part[i * 3 + 1]; s2 += part[i * 3 + 2]; }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; red[2][warp] = s2; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+            tot[threadIdx.x] = s;
+        }
     }
     __syncthreads();
     const float inv = tot[1] > 0.f ? 1.f / tot[1] : 0.f;
@@ -88,7 +98,7 @@ __global__ void __launch_bounds__(256) loss_final_kernel(const float* __restrict
 
 using namespace gptst;
 
-extern "C" int gptst_loss_parts(void) { return 148; }
+extern "C" int gptst_loss_parts(void) { return 4 * 148; }
 
 extern "C" int gptst_pretrain_loss(const float* o, const float* src, const long long* inv_mask, const float* prob,
                                    const float* hs, float* d_o, float* d_prob, float* part, float* out, long n_cells, int ibd,

@@ -750,3 +750,100 @@ extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, c
     gptst::sm::sum_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
     return (int)cudaGetLastError();
 }
+
+// Backward of the score head:  dz = prob * (dprob - <prob, dprob>) ;  dh = dz W3 ;  dW3_part[cta] = dz^T h ;  db3_part[cta] = sum dz
+// (library version: two 187 us split-K GEMMs with K = B*T*N).  CTA = 256 rows, thread = row for dz / dh, then the CTA's
+// (H x D + H) partial with h and dz staged in shared memory.  part: (ctas, H*D + H), summed by the caller.
+namespace gptst {
+namespace sm {
+template <int D>
+__global__ void __launch_bounds__(256) score_head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ W3,
+                                                             const float* __restrict__ prob, const float* __restrict__ dprob,
+                                                             float* __restrict__ dh, float* __restrict__ part, long rows, int H) {
+    constexpr int LDS = D + 1;
+    extern __shared__ __align__(16) float sh[];
+    float* tile = sh;                       // [256][D+1]  h rows
+    float* Ws = tile + 256 * LDS;           // [H][D]
+    float* dzs = Ws + kMaxH * D;            // [256][kMaxH+1]
+    const int tid = threadIdx.x;
+    const long r0 = (long)blockIdx.x * 256;
+    for (int i = tid; i < H * D; i += 256) Ws[i] = W3[i];
+    for (int i = tid; i < 256 * (D / 4); i += 256) {
+        const int r = i / (D / 4), q = i % (D / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < rows) v = *reinterpret_cast<const float4*>(h + (r0 + r) * D + 4 * q);
+        float* dst = tile + r * LDS + 4 * q;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    // dz of this thread's row
+    float dz[kMaxH];
+    {
+        const long r = r0 + tid;
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxH; ++j) {
+            float p = 0.f, g = 0.f;
+            if (j < H && r < rows) { p = prob[r * H + j]; g = dprob[r * H + j]; }
+            dz[j] = p;
+            dot = fmaf(p, g, dot);
+            dzs[tid * (kMaxH + 1) + j] = g;          // temporarily dprob
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxH; ++j) {
+            dz[j] = dz[j] * (dzs[tid * (kMaxH + 1) + j] - dot);
+            dzs[tid * (kMaxH + 1) + j] = dz[j];
+        }
+    }
+    __syncthreads();
+    // dh row = dz . W3  (written through the row's own slot of the h tile? no: h is still needed -> straight to global)
+    if (dh && r0 + tid < rows) {
+        float* out = dh + (r0 + tid) * D;
+        for (int d0 = 0; d0 < D; d0 += 4) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kMaxH; ++j) {
+                if (j < H) {
+                    const float z = dz[j];
+                    o.x = fmaf(z, Ws[j * D + d0], o.x); o.y = fmaf(z, Ws[j * D + d0 + 1], o.y);
+                    o.z = fmaf(z, Ws[j * D + d0 + 2], o.z); o.w = fmaf(z, Ws[j * D + d0 + 3], o.w);
+                }
+            }
+            *reinterpret_cast<float4*>(out + d0) = o;
+        }
+    }
+    // partial dW3 (H x D) and db3 (H) of this CTA
+    float* po = part + (size_t)blockIdx.x * (H * D + H);
+    for (int i = tid; i < H * D + H; i += 256) {
+        float s = 0.f;
+        if (i < H * D) {
+            const int j = i / D, d = i % D;
+            for (int r = 0; r < 256; ++r) s = fmaf(dzs[r * (kMaxH + 1) + j], tile[r * LDS + d], s);
+        } else {
+            const int j = i - H * D;
+            for (int r = 0; r < 256; ++r) s += dzs[r * (kMaxH + 1) + j];
+        }
+        po[i] = s;
+    }
+}
+}  // namespace sm
+}  // namespace gptst
+
+extern "C" int gptst_score_head_bwd_parts(long rows) { return (int)((rows + 255) / 256); }
+extern "C" int gptst_score_head_bwd(const float* h, const float* W3, const float* prob, const float* dprob, float* dh, float* part,
+                                    long rows, int D, int H, void* stream) {
+    if (!h || !W3 || !prob || !dprob || !part || rows <= 0) return -1;
+    if (H < 1 || H > gptst::kMaxH || (D != 64 && D != 128)) return -2;
+    const size_t smem = ((size_t)256 * (D + 1) + (size_t)gptst::kMaxH * D + 256 * (size_t)(gptst::kMaxH + 1)) * 4;
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    cudaError_t e;
+    if (D == 64) {
+        e = cudaFuncSetAttribute(gptst::sm::score_head_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        gptst::sm::score_head_bwd_kernel<64><<<grid, 256, smem, (cudaStream_t)stream>>>(h, W3, prob, dprob, dh, part, rows, H);
+    } else {
+        e = cudaFuncSetAttribute(gptst::sm::score_head_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        gptst::sm::score_head_bwd_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(h, W3, prob, dprob, dh, part, rows, H);
+    }
+    return (int)cudaGetLastError();
+}

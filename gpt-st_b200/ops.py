@@ -431,8 +431,8 @@ def lowrank_table(te, pool):
 
 
 class _ScoreHead(torch.autograd.Function):
-    """prob = softmax(h W3^T + b3): forward in one kernel (critical front of the adaptive phase); the backward (KL branch, on the
-    scorer's side stream) uses the closed forms with library ops."""
+    """prob = softmax(h W3^T + b3): forward in one kernel (critical front of the adaptive phase), backward in one kernel plus
+    the partial sum (the library version needed two 187 us split-K GEMMs with K = B*T*N)."""
 
     @staticmethod
     def forward(ctx, h, W3, b3):
@@ -448,10 +448,16 @@ class _ScoreHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dprob):
         h, W3, prob = ctx.saved_tensors
-        dz = prob * (dprob - (prob * dprob).sum(-1, keepdim=True))          # softmax backward
-        dz2 = dz.reshape(-1, dz.shape[-1])
-        dh = (dz2 @ W3).view_as(h) if ctx.needs_input_grad[0] else None
-        return dh, dz2.t() @ h.reshape(-1, h.shape[-1]), dz2.sum(0)
+        D, H = h.shape[-1], W3.shape[0]
+        rows = h.numel() // D
+        L = _lib.lib()
+        parts = L.gptst_score_head_bwd_parts(rows)
+        part = torch.empty((parts, H * D + H), device=h.device, dtype=torch.float32)
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        _lib.check(L.gptst_score_head_bwd(_p(h), _p(W3), _p(prob), _p(dprob.contiguous()), _p(dh), _p(part), rows, D, H, _stream()),
+                   "gptst_score_head_bwd")
+        (tot,) = sum_partials(part)
+        return dh, tot[:H * D].view(H, D), tot[H * D:]
 
 
 def score_head(h, W3, b3):

@@ -165,6 +165,11 @@ int gptst_mn_bwd(const float* A, const float* dM, float* dA, int N, int Ht, int 
 int gptst_score_head_fwd(const float* h, const float* W3, const float* b3, float* prob, long rows, int D, int H, void* stream);
 /* sums the (parts[k], numel[k]) partial buffers of up to 8 tensors in one launch, fixed order: outs[k][i] = sum_p ins[k][p][i]
  * (host arrays of device pointers / sizes; the values are copied into the launch arguments)                                */
+/* backward of the score head: dh (rows,D) = dz W3 with dz = prob*(dprob - <prob,dprob>); part (gptst_score_head_bwd_parts(rows),
+ * H*D + H) = per-CTA partials of dW3 = dz^T h and db3 = sum dz, summed by the caller; dh may be NULL                        */
+int gptst_score_head_bwd_parts(long rows);
+int gptst_score_head_bwd(const float* h, const float* W3, const float* prob, const float* dprob, float* dh, float* part,
+                         long rows, int D, int H, void* stream);
 int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n, void* stream);
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
