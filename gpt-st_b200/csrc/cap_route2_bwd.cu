@@ -143,9 +143,8 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
             mma_f16(zh[0], vh, p0h[0], p0h[1]);
             mma_f16(zh[1], vh, p1h[0], p1h[1]);
         }
-        // C fragment of tile 0: (h0, node n0+2t) (h0, n0+2t+1) (h1, ..) -- but tile 0 holds NODES g?  No: the B operand's n index
-        // is the node, so tile 0 covers nodes n0..n0+7 = rows g of the Z fragments, and its C columns 2t, 2t+1 are nodes
-        // n0+2t, n0+2t+1: the same layout as cf / dc.
+        // The B operand's n index is the node (tile 0 = nodes n0..n0+7 = rows g of the Z fragments), so the C fragment
+        // (h0 / h1, nodes n0+2t, n0+2t+1 | +8 for tile 1) has exactly the layout of cf / dc.
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             dc[i] += (zh[0][i] + zl[0][i]) * sc.y;
