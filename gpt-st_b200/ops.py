@@ -298,6 +298,34 @@ class _AdaptiveProj(torch.autograd.Function):
         return dX, dW.view_as(W), db.view(W.shape[:-2] + (W.shape[-1],)), None, None
 
 
+class _SharedLinear(torch.autograd.Function):
+    """y = x W^T + b with ONE shared (D, D) weight in nn.Linear layout, through the grouped-projection kernels with a single
+    group (rows = every cell).  Used by the eval-path fusion gate (reference model/Model.py:5-18)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec):
+        x = x.contiguous()
+        Wt = weight.t().contiguous().unsqueeze(0)              # [in][out], one group
+        D = x.shape[-1]
+        y = gproj_fwd(x.view(1, 1, -1, D), Wt, bias.contiguous().view(1, D), None, node_grouped=False, act=False, prec=prec)
+        ctx.save_for_backward(x, Wt)
+        ctx.prec = prec
+        return y.view(x.shape[:-1] + (D,))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wt = ctx.saved_tensors
+        D = x.shape[-1]
+        dX, dW, db, _ = gproj_bwd(dy.contiguous().view(1, 1, -1, D), None, x.view(1, 1, -1, D), Wt, node_grouped=False, act=False,
+                                  prec=ctx.prec, want_dres=False)
+        return dX.view_as(x), dW.view(D, D).t(), db.view(D), None
+
+
+def shared_linear(x, weight, bias, prec=None):
+    """nn.Linear(D, D) on (..., D) CUDA tensors through the sm_100a projection kernels (D = 64 or 128)."""
+    return _SharedLinear.apply(x, weight, bias, default_precision() if prec is None else prec)
+
+
 def node_adaptive_proj(x, Wn, bn, prec=None):
     """y[b,t,n,:] = LReLU(x[b,t,n,:] . Wn[n] + bn[n])      GPTST.py:24-27"""
     return _AdaptiveProj.apply(x, Wn, bn, True, default_precision() if prec is None else prec)

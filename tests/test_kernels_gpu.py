@@ -424,3 +424,32 @@ def test_score_head_matches_torch():
     check(hc.grad, h.grad, 1e-5, "score head dh")
     check(Wc.grad, W3.grad, 1e-5, "score head dW3")
     check(bc.grad, b3.grad, 1e-5, "score head db3")
+
+
+@pytest.mark.parametrize("prec", [3])
+def test_eval_glue_fusion_matches_reference_formula(prec):
+    """Row f4: the fusion gate of Enhance_model (model/Model.py:5-18,106-109) through the projection kernels vs the plain
+    nn.Linear formula in fp64, forward and all gradients; state_dict names as in the reference."""
+    from gptst_b200.fusion import EvalGlue
+    torch.manual_seed(11)
+    B, N, D = 3, 37, 64
+    glue = EvalGlue(1, D).cuda()
+    assert set(glue.state_dict()) == {"fusion.HS_fc.weight", "fusion.HS_fc.bias", "fusion.HT_fc.weight", "fusion.HT_fc.bias",
+                                      "fusion.output_fc.weight", "fusion.output_fc.bias", "lin_test.weight", "lin_test.bias"}
+    src = rnd(B, 12, N, 3, seed=1)
+    x = rnd(B, 12, N, D, seed=2).requires_grad_()
+    P = {k: v.detach().double().cpu().requires_grad_() for k, v in glue.state_dict().items()}
+    y = src[..., :1] @ P["lin_test.weight"].t() + P["lin_test.bias"]
+    xs = x @ P["fusion.HS_fc.weight"].t() + P["fusion.HS_fc.bias"]
+    xt = y @ P["fusion.HT_fc.weight"].t() + P["fusion.HT_fc.bias"]
+    z = torch.sigmoid(xs + xt)
+    want = (z * x + (1 - z) * y) @ P["fusion.output_fc.weight"].t() + P["fusion.output_fc.bias"]
+    g = rnd(B, 12, N, D, seed=3)
+    want.backward(g)
+    xc = x.detach().float().cuda().requires_grad_()
+    got = glue(src.float().cuda(), xc)
+    check(got, want.detach(), 5e-5, "fusion out")
+    got.backward(g.float().cuda())
+    check(xc.grad, x.grad, 2e-4, "fusion dx")
+    for k, p in glue.named_parameters():
+        check(p.grad, P[k].grad, 2e-4, "fusion grad " + k)
