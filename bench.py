@@ -291,10 +291,11 @@ def kernel_rooflines(N, D, B, peak, iters=20):
         algo = 5 * A + 2 * 4 * B * 12 * D * D     # dY, Y, X in; dX, dRes out; W_bt in, dW_bt out
         out["gproj_bwd_time_grouped"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
                                          "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
-        ms = timeit(lambda s: ops.tmix_bwd(s[0], s[1], Mn, s[2], prec))
-        algo = 4 * A                              # dy, x in; dx read-modify-write
-        out["tmix_bwd"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
-                           "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
+        if D == 64:                               # the fused mix backward exists for D = 64 (D = 128 uses tmix + tmix_dM)
+            ms = timeit(lambda s: ops.tmix_bwd(s[0], s[1], Mn, s[2], prec))
+            algo = 4 * A                          # dy, x in; dx read-modify-write
+            out["tmix_bwd"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
+                               "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
     return out
 
 
