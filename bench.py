@@ -204,6 +204,35 @@ def workload_config(name, B, world, epoch):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def time_graph_replays(fns, iters=20):
+    """Median CUDA-event time of replaying one captured graph per rotating input set (fns[i]() is captured once).  The product
+    runs these kernels inside the captured step; timing eager Python calls instead leaves host gaps (tensor allocation, ctypes)
+    between event record and launch that are not kernel time."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for f in fns:
+            f()                                  # warm-up / allocator
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs = []
+    for f in fns:
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            f()
+        graphs.append(g_)
+    times = []
+    for i in range(3 + iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graphs[i % len(graphs)].replay()
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    return statistics.median(times)
+
+
 def cap_forward_roofline(N, D, B, iters=20):
     """cap forward (GPTST.py:100-141) timed alone with CUDA events on the launching stream, on rotating buffer
     sets larger than L2 so every launch reads x from HBM.  Algorithmic bytes: 4*B*T*N*(2D+H)."""
@@ -220,18 +249,8 @@ def cap_forward_roofline(N, D, B, iters=20):
     Wn = torch.randn(N, D, D, device=dev, generator=g) * D ** -0.5
     bn = torch.rand(N, D, device=dev, generator=g)
     prec = ops.default_precision()
-    times = []
     with torch.no_grad():
-        for i in range(3 + iters):
-            x = xs[i % nset]
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.cap_core(x, Wp, bp, dadj, dyn, Wn, bn, 2, prec)
-            e1.record()
-            e1.synchronize()
-            if i >= 3:
-                times.append(e0.elapsed_time(e1))
-    ms = statistics.median(times)
+        ms = time_graph_replays([(lambda x=x: ops.cap_core(x, Wp, bp, dadj, dyn, Wn, bn, 2, prec)) for x in xs], iters)
     algo = 4 * B * T * N * (2 * D + H)
     return algo, ms
 
@@ -246,17 +265,9 @@ def hypertem_forward_time(N, D, B, iters=20):
     W = torch.randn(B, 12, D, D, device=dev, generator=g) * D ** -0.5
     b = torch.rand(B, 12, D, device=dev, generator=g)
     prec = ops.default_precision()
-    times = []
     with torch.no_grad():
-        for i in range(3 + iters):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.hypertem_core(xs[i % nset], Mn, W, b, prec)
-            e1.record()
-            e1.synchronize()
-            if i >= 3:
-                times.append(e0.elapsed_time(e1))
-    return 8 * B * T_STEPS * N * D, statistics.median(times)
+        ms = time_graph_replays([(lambda x=x: ops.hypertem_core(x, Mn, W, b, prec)) for x in xs], iters)
+    return 8 * B * T_STEPS * N * D, ms
 
 
 def kernel_rooflines(N, D, B, peak, iters=20):
@@ -274,16 +285,7 @@ def kernel_rooflines(N, D, B, peak, iters=20):
     out = {}
 
     def timeit(fn):
-        ts = []
-        for i in range(3 + iters):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn(sets[i % nset])
-            e1.record()
-            e1.synchronize()
-            if i >= 3:
-                ts.append(e0.elapsed_time(e1))
-        return statistics.median(ts)
+        return time_graph_replays([(lambda st=st: fn(st)) for st in sets], iters)
 
     with torch.no_grad():
         # the call also sums its (splits == 1) partials: a view, no extra kernel
