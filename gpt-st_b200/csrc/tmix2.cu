@@ -19,6 +19,9 @@ namespace tm2 {
 
 using namespace hf;
 constexpr int T = 12, D = 64;
+#ifndef TMIX_MINB
+#define TMIX_MINB 3
+#endif
 
 // Shared-memory layout per warp: two 16-row tiles (dy, x) of 272-byte slots; rows 12..15 stay zero.  Rows are staged with
 // 16-byte cp.async chunks (two full 256-byte rows per warp request: 4 cache lines per request instead of the 8 that a
@@ -35,7 +38,7 @@ __device__ __forceinline__ void stage_tile(unsigned char* tile, const float* bas
 }
 
 template <int PREC>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, TMIX_MINB)
 tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ M,
                 float* __restrict__ dx_io, float* __restrict__ dM_part, int B, int N, int bps) {
     extern __shared__ __align__(128) unsigned char smraw[];
