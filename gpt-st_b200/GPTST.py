@@ -104,11 +104,20 @@ class cap(nn.Module):
         dyn = ops.lowrank_table(time_eb, self.t_adj)                    # einsum("bd,dhk->bhk")
         Wn = ops.lowrank_table(node_embeddings, self.weights_spa)       # einsum("nd,dio->nio")
         bn = ops.lowrank_table(node_embeddings, self.bias_spa)
-        return dadj, dyn, Wn, bn
+        if not dadj.is_cuda:
+            return dadj, dyn, Wn, bn, None
+        # stride-0 (P, ...) views of the five parameter-side inputs: the block's backward returns its per-CTA gradient partials
+        # for them and the sums run HERE (this stream) as the expands' backward, off the main chain (ops.expand_partials)
+        B, T, H, N = dadj.shape
+        exp = ops.cap_expand(self.ln_p.weight, self.ln_p.bias, dyn, Wn, bn, B, T, N, self.dim, H)
+        return dadj, dyn, Wn, bn, exp
 
     def forward(self, x, node_embeddings, time_eb, teb, tables=None):
-        dadj, dyn, Wn, bn = tables if tables is not None else self.tables(node_embeddings, time_eb, teb)
-        out, c = ops.cap_core(x, self.ln_p.weight, self.ln_p.bias, dadj, dyn, Wn, bn, self.num_route)
+        dadj, dyn, Wn, bn, exp = tables if tables is not None else self.tables(node_embeddings, time_eb, teb)
+        if exp is None:
+            out, c = ops.cap_core(x, self.ln_p.weight, self.ln_p.bias, dadj, dyn, Wn, bn, self.num_route)
+        else:
+            out, c = ops.cap_core(x, exp[0], exp[1], dadj, exp[2], exp[3], exp[4], self.num_route, expanded=True)
         return out, c.unsqueeze(-1), dyn.detach()
 
 
@@ -128,6 +137,9 @@ class hyperTem(nn.Module):
         Mn = ops.mix_matrix(A) if A.is_cuda else torch.einsum("nht,nhs->nts", A, A)   # two hops, no nonlinearity in between
         W = ops.lowrank_table(time_eb, self.weights_pool)               # einsum("btd,dio->btio")
         bias = ops.lowrank_table(time_eb, self.bias_pool)
+        if Mn.is_cuda:
+            # (P, N, T, T) stride-0 view: the dM_n partials of the backward are summed on this stream (ops.expand_partials)
+            Mn = ops.expand_partials(Mn, ops.hypertem_partial_count(time_eb.shape[0], Mn.shape[0], W.shape[-1]))
         return Mn, W, bias
 
     def forward(self, eb, node_embeddings, time_eb, tables=None):
@@ -222,7 +234,8 @@ class STHCN(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(st)
             for t in tb:
-                t.record_stream(main)
+                if isinstance(t, torch.Tensor):          # (the expanded views of a cap share these tensors' storage)
+                    t.record_stream(main)
             pro["ht"].append(tb)
             pro["ht_ev"].append(ev)
         for i in range(2):
@@ -236,7 +249,8 @@ class STHCN(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(st)
             for t in tb:
-                t.record_stream(main)
+                if isinstance(t, torch.Tensor):          # (the expanded views of a cap share these tensors' storage)
+                    t.record_stream(main)
             pro["cap"].append(tb)
             pro["cap_ev"].append(ev)
         return pro
@@ -455,7 +469,10 @@ class Hypergraph_decoder(nn.Module):
 
     def forward(self, source, flow_encode_eb, pro=None):
         flow_decode, _, _ = self.STHCN_decode(source, flow_encode_eb, pro)
-        return self.dim_flow_out(flow_decode), flow_decode
+        lin = self.dim_flow_out
+        if flow_decode.is_cuda and lin.out_features <= 4:
+            return ops.proj_out(flow_decode, lin.weight, lin.bias), flow_decode      # one streaming kernel each way
+        return lin(flow_decode), flow_decode
 
 
 class GPTST_Model(nn.Module):

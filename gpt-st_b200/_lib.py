@@ -28,6 +28,7 @@ SIGNATURES = {
     "gptst_cap_recon": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_e1": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon_hop": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_recon_hop_fused": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_dv_dcr": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd_parts": (_i, [_i]),
@@ -62,6 +63,9 @@ SIGNATURES = {
     "gptst_affine1_fwd": (_i, [_f, _f, _f, _f, _l, _i, _f]),
     "gptst_affine1_bwd_parts": (_i, [_l]),
     "gptst_affine1_bwd": (_i, [_f, _f, _f, _l, _i, _i, _f]),
+    "gptst_proj_out_fwd": (_i, [_f, _f, _f, _f, _l, _i, _i, _f]),
+    "gptst_proj_out_bwd_parts": (_i, [_l]),
+    "gptst_proj_out_bwd": (_i, [_f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
     "gptst_loss_parts": (_i, []),
     "gptst_pretrain_loss": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _i, C.c_float, C.c_float, C.c_float,
                                 C.c_float, _f]),

@@ -46,24 +46,54 @@ __global__ void __launch_bounds__(256) cap_hop_e1_kernel(const float* __restrict
     }
 }
 
-// grid (B*T, ychunks), 256 threads
-template <int D>
+// grid (B*T, ychunks), 256 threads.  FUSE_E1: E1[b] is recomputed by every slab CTA of the sample (123k MACs, s_b read from
+// L2) instead of being read from a separate hop_e1 launch; the t == 0 CTA writes it out for the backward pass.
+template <int D, bool FUSE_E1>
 __global__ void __launch_bounds__(256) cap_recon_hop_kernel(const float* __restrict__ c, const float* __restrict__ s,
-                                                            const float* __restrict__ dyn, const float* __restrict__ e1,
+                                                            const float* __restrict__ dyn, float* __restrict__ e1,
                                                             float* __restrict__ v, float* __restrict__ recon, int T, int N,
                                                             int H, int HT) {
     extern __shared__ __align__(16) float smem[];
+    const int K = T * H;
     float* E1 = smem;                      // [HT][D]
-    float* dy = E1 + (size_t)HT * D;       // [HT][H]   dyn[b][:, t*H .. t*H+H)
-    float* vs = dy + (size_t)HT * H;       // [H][D]
+    float* dy = E1 + (size_t)HT * D;       // FUSE_E1: [HT][K] (all of dyn_b) ; else [HT][H] = dyn[b][:, t*H .. t*H+H)
+    float* vs = dy + (size_t)HT * (FUSE_E1 ? K : H);       // [H][D]
     float* cs = vs + (size_t)H * D;        // [H][N]  the slab's incidence (staged up front: its latency hides under the hop)
     const int slab = blockIdx.x, b = slab / T, tt = slab % T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int K = T * H;
+    const int dstride = FUSE_E1 ? K : H, doff = FUSE_E1 ? tt * H : 0;    // dy[ht * dstride + doff + h] = dyn[b][ht][t*H + h]
     for (int i = tid; i < H * N; i += 256) cs[i] = c[(size_t)slab * H * N + i];
-    for (int i = tid; i < HT * D / 4; i += 256)
-        reinterpret_cast<float4*>(E1)[i] = reinterpret_cast<const float4*>(e1 + (size_t)b * HT * D)[i];
-    for (int i = tid; i < HT * H; i += 256) dy[i] = dyn[((size_t)b * HT + i / H) * K + tt * H + (i % H)];
+    if (FUSE_E1) {
+        for (int i = tid; i < HT * K; i += 256) dy[i] = dyn[(size_t)b * HT * K + i];
+        __syncthreads();
+        // E1[ht][d] = phi( sum_k dyn[ht][k] (s_b[k][d] + tau_k) ): thread = (column d, 4 rows ht = g, g + HT/4, ...)
+        const int d = tid % D, grp = tid / D;          // 256 / D groups
+        constexpr int G = 256 / D;
+        const float* sb = s + (size_t)b * K * D + d;
+        for (int h0 = grp; h0 < HT; h0 += 4 * G) {
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int k = 0; k < K; ++k) {
+                const float sv = sb[(size_t)k * D] + (float)(k / H + 1) / 12.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (h0 + j * G < HT) a[j] = fmaf(dy[(h0 + j * G) * K + k], sv, a[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ht = h0 + j * G;
+                if (ht < HT) {
+                    const float val = lrelu(a[j]);
+                    E1[ht * D + d] = val;
+                    if (tt == 0 && blockIdx.y == 0) e1[((size_t)b * HT + ht) * D + d] = val;
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < HT * D / 4; i += 256)
+            reinterpret_cast<float4*>(E1)[i] = reinterpret_cast<const float4*>(e1 + (size_t)b * HT * D)[i];
+        for (int i = tid; i < HT * H; i += 256) dy[i] = dyn[((size_t)b * HT + i / H) * K + tt * H + (i % H)];
+    }
     __syncthreads();
     for (int h = warp; h < H; h += 8) {
         float r[D / 32];
@@ -72,7 +102,7 @@ __global__ void __launch_bounds__(256) cap_recon_hop_kernel(const float* __restr
         for (int j = 0; j < D / 32; ++j) {
             const int d = lane + 32 * j;
             float a = 0.f;
-            for (int ht = 0; ht < HT; ++ht) a = fmaf(dy[ht * H + h], E1[ht * D + d], a);
+            for (int ht = 0; ht < HT; ++ht) a = fmaf(dy[ht * dstride + doff + h], E1[ht * D + d], a);
             r[j] = lrelu(a) + s[((size_t)slab * H + h) * D + d];
             q += r[j] * r[j];
         }
@@ -155,10 +185,12 @@ __global__ void __launch_bounds__(256) cap_hop_bwd_cols_kernel(const float* __re
                                                                float* __restrict__ ddyn_part, int B, int T, int D, int H,
                                                                int HT) {
     extern __shared__ __align__(16) float smem[];
-    const int K = T * H, C = kE1Cols;
-    float* Ss = smem;                         // [K][C]   s + tau
-    float* P2 = Ss + (size_t)K * C;           // [K][C]   dpre2
-    float* E1 = P2 + (size_t)K * C;           // [HT][C]
+    // Ss / P2 rows are padded to C + 1 floats: the ddyn pass below walks them with the lane index on k, and a stride of 16
+    // floats put every other row on the same bank (16-way conflicts = most of this kernel's former 32 us)
+    const int K = T * H, C = kE1Cols, CP = kE1Cols + 1;
+    float* Ss = smem;                         // [K][CP]  s + tau
+    float* P2 = Ss + (size_t)K * CP;          // [K][CP]  dpre2
+    float* E1 = P2 + (size_t)K * CP;          // [HT][C]
     float* D1 = E1 + (size_t)HT * C;          // [HT][C]  dpre1
     float* dy = D1 + (size_t)HT * C;          // [HT][K+1]
     const int tid = threadIdx.x, b = blockIdx.x, c0 = blockIdx.y * C;
@@ -167,9 +199,11 @@ __global__ void __launch_bounds__(256) cap_hop_bwd_cols_kernel(const float* __re
         const size_t off = ((size_t)b * K + k) * D + c0 + 4 * q;
         float4 v = *reinterpret_cast<const float4*>(s + off);
         const float tau = (float)(k / H + 1) / 12.f;
-        v.x += tau; v.y += tau; v.z += tau; v.w += tau;
-        *reinterpret_cast<float4*>(Ss + k * C + 4 * q) = v;
-        *reinterpret_cast<float4*>(P2 + k * C + 4 * q) = *reinterpret_cast<const float4*>(dpre2 + off);
+        const float4 p = *reinterpret_cast<const float4*>(dpre2 + off);
+        float* sd = Ss + k * CP + 4 * q;
+        float* pd = P2 + k * CP + 4 * q;
+        sd[0] = v.x + tau; sd[1] = v.y + tau; sd[2] = v.z + tau; sd[3] = v.w + tau;
+        pd[0] = p.x; pd[1] = p.y; pd[2] = p.z; pd[3] = p.w;
     }
     for (int i = tid; i < HT * (C / 4); i += 256) {
         const int ht = i / (C / 4), q = i % (C / 4);
@@ -183,12 +217,12 @@ __global__ void __launch_bounds__(256) cap_hop_bwd_cols_kernel(const float* __re
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int k = 0;
         for (; k + 3 < K; k += 4) {
-            a0 = fmaf(drow[k], P2[k * C + col], a0);
-            a1 = fmaf(drow[k + 1], P2[(k + 1) * C + col], a1);
-            a2 = fmaf(drow[k + 2], P2[(k + 2) * C + col], a2);
-            a3 = fmaf(drow[k + 3], P2[(k + 3) * C + col], a3);
+            a0 = fmaf(drow[k], P2[k * CP + col], a0);
+            a1 = fmaf(drow[k + 1], P2[(k + 1) * CP + col], a1);
+            a2 = fmaf(drow[k + 2], P2[(k + 2) * CP + col], a2);
+            a3 = fmaf(drow[k + 3], P2[(k + 3) * CP + col], a3);
         }
-        for (; k < K; ++k) a0 = fmaf(drow[k], P2[k * C + col], a0);
+        for (; k < K; ++k) a0 = fmaf(drow[k], P2[k * CP + col], a0);
         D1[ht * C + col] = lrelu_grad(E1[ht * C + col], (a0 + a1) + (a2 + a3));     // sign(E1) == sign(pre1)
     }
     __syncthreads();
@@ -204,7 +238,7 @@ __global__ void __launch_bounds__(256) cap_hop_bwd_cols_kernel(const float* __re
         const int ht = i / K, k = i % K;
         float a = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < C; ++cc) a = fmaf(E1[ht * C + cc], P2[k * C + cc], fmaf(D1[ht * C + cc], Ss[k * C + cc], a));
+        for (int cc = 0; cc < C; ++cc) a = fmaf(E1[ht * C + cc], P2[k * CP + cc], fmaf(D1[ht * C + cc], Ss[k * CP + cc], a));
         dp[i] = a;
     }
 }
@@ -226,30 +260,43 @@ extern "C" int gptst_cap_hop_e1(const float* s, const float* dyn, float* e1, int
     return (int)cudaGetLastError();
 }
 
-extern "C" int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const float* e1, float* v,
-                                   float* recon, int B, int T, int N, int D, int H, int HT, void* stream) {
-    if (!c || !s || !dyn || !e1 || !v || !recon || B <= 0 || T <= 0 || N <= 0 || HT <= 0) return -1;
-    if (H < 1 || H > kMaxH) return -2;
-    cudaStream_t st = (cudaStream_t)stream;
+template <bool FUSE>
+static int launch_recon_hop(const float* c, const float* s, const float* dyn, float* e1, float* v, float* recon, int B, int T,
+                            int N, int D, int H, int HT, cudaStream_t st) {
     const int npc = 256 / (D / 4);
     int ychunks = (N + npc - 1) / npc;
     int want = (592 + B * T - 1) / (B * T);
     if (ychunks > want) ychunks = want;
     if (ychunks < 1) ychunks = 1;
-    const size_t smem = ((size_t)HT * D + (size_t)HT * H + (size_t)H * D + (size_t)H * N) * 4;
+    const size_t smem = ((size_t)HT * D + (size_t)HT * (FUSE ? T * H : H) + (size_t)H * D + (size_t)H * N) * 4;
     if (smem > kSmemMax) return -2;
     dim3 grid(B * T, ychunks);
     cudaError_t e;
     if (D == 64) {
-        e = cudaFuncSetAttribute(cap_recon_hop_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(cap_recon_hop_kernel<64, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        cap_recon_hop_kernel<64><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
+        cap_recon_hop_kernel<64, FUSE><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
     } else if (D == 128) {
-        e = cudaFuncSetAttribute(cap_recon_hop_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(cap_recon_hop_kernel<128, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        cap_recon_hop_kernel<128><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
+        cap_recon_hop_kernel<128, FUSE><<<grid, 256, smem, st>>>(c, s, dyn, e1, v, recon, T, N, H, HT);
     } else return -2;
     return (int)cudaGetLastError();
+}
+
+extern "C" int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const float* e1, float* v,
+                                   float* recon, int B, int T, int N, int D, int H, int HT, void* stream) {
+    if (!c || !s || !dyn || !e1 || !v || !recon || B <= 0 || T <= 0 || N <= 0 || HT <= 0) return -1;
+    if (H < 1 || H > kMaxH) return -2;
+    return launch_recon_hop<false>(c, s, dyn, const_cast<float*>(e1), v, recon, B, T, N, D, H, HT, (cudaStream_t)stream);
+}
+
+// the same with hop_e1 folded in: e1 (B,HT,D) is an OUTPUT (kept for the backward pass); one launch instead of two
+extern "C" int gptst_cap_recon_hop_fused(const float* c, const float* s, const float* dyn, float* e1, float* v, float* recon,
+                                         int B, int T, int N, int D, int H, int HT, void* stream) {
+    if (!c || !s || !dyn || !e1 || !v || !recon || B <= 0 || T <= 0 || N <= 0 || HT <= 0) return -1;
+    if (H < 1 || H > kMaxH) return -2;
+    return launch_recon_hop<true>(c, s, dyn, e1, v, recon, B, T, N, D, H, HT, (cudaStream_t)stream);
 }
 
 extern "C" int gptst_cap_hop_bwd_parts(int D) { return D / kE1Cols; }
@@ -263,7 +310,7 @@ extern "C" int gptst_cap_hop_bwd2(const float* s, const float* dyn, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const int K = T * H;
     const size_t smem1 = ((size_t)HT * D + (size_t)HT * H) * 4;
-    const size_t smem2 = ((size_t)2 * K * kE1Cols + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
+    const size_t smem2 = ((size_t)2 * K * (kE1Cols + 1) + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
     if (smem1 > 48 * 1024 || smem2 > kSmemMax) return -2;
     if (D == 64) cap_hop_bwd_rows_kernel<64><<<B * T, 256, smem1, st>>>(s, dyn, e1, dv, dr_tmp, dpre2_tmp, T, H, HT);
     else if (D == 128) cap_hop_bwd_rows_kernel<128><<<B * T, 256, smem1, st>>>(s, dyn, e1, dv, dr_tmp, dpre2_tmp, T, H, HT);
@@ -282,7 +329,7 @@ extern "C" int gptst_cap_hop_bwd_cols(const float* s, const float* dyn, const fl
     if (!s || !dyn || !e1 || !dr || !dpre2 || !ds || !ddyn_part || B <= 0 || T <= 0 || HT <= 0) return -1;
     if (H < 1 || H > kMaxH || D % kE1Cols != 0) return -2;
     const int K = T * H;
-    const size_t smem2 = ((size_t)2 * K * kE1Cols + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
+    const size_t smem2 = ((size_t)2 * K * (kE1Cols + 1) + (size_t)2 * HT * kE1Cols + (size_t)HT * (K + 1)) * 4;
     if (smem2 > kSmemMax) return -2;
     cudaError_t e = cudaFuncSetAttribute(cap_hop_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return (int)e;

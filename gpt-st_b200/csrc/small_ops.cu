@@ -702,9 +702,11 @@ struct SumSegs {
     float* out[8];
     long numel[8];
     int parts[8];
-    long start[9];     // prefix sums of numel (in float4 units where possible is not assumed: scalar elements)
+    long start[9];     // prefix sums of numel (scalar elements, or float4 units on the vectorised path)
     int n;
 };
+// thread = one element (VEC = 1) or one float4 of elements (VEC = 4; start[] / numel[] are then in float4 units)
+template <int VEC>
 __global__ void __launch_bounds__(256) sum_partials_kernel(SumSegs s) {
     const long total = s.start[s.n];
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
@@ -712,16 +714,49 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(SumSegs s) {
 #pragma unroll
         for (int j = 1; j < 8; ++j) k += (j < s.n && i >= s.start[j]);
         const long e = i - s.start[k];
+        const long stride = s.numel[k];
+        const int parts = s.parts[k];
+        if (VEC == 4) {
+            const float4* p = reinterpret_cast<const float4*>(s.in[k]) + e;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            int q = 0;
+            for (; q + 1 < parts; q += 2) {
+                const float4 u = p[(long)q * stride], v = p[(long)(q + 1) * stride];
+                a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+                a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+            }
+            if (q < parts) { const float4 u = p[(long)q * stride]; a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w; }
+            reinterpret_cast<float4*>(s.out[k])[e] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+        } else {
+            const float* p = s.in[k] + e;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int q = 0;
+            for (; q + 3 < parts; q += 4) {
+                a0 += p[(long)q * stride]; a1 += p[(long)(q + 1) * stride]; a2 += p[(long)(q + 2) * stride]; a3 += p[(long)(q + 3) * stride];
+            }
+            for (; q < parts; ++q) a0 += p[(long)q * stride];
+            s.out[k][e] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+// few elements, many partials (per-CTA partials of a small parameter gradient): one WARP per element, lanes stride over the
+// partials, shuffle tree at the end -- a thread walking hundreds of partials serially is pure load latency (38 us for the
+// score head's 650 x 510 case)
+__global__ void __launch_bounds__(256) sum_partials_warp_kernel(SumSegs s) {
+    const long total = s.start[s.n];
+    const int lane = threadIdx.x & 31;
+    for (long i = ((long)blockIdx.x * 256 + threadIdx.x) >> 5; i < total; i += (long)gridDim.x * 8) {   // warp-uniform
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) k += (j < s.n && i >= s.start[j]);
+        const long e = i - s.start[k];
         const float* p = s.in[k] + e;
         const long stride = s.numel[k];
         const int parts = s.parts[k];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int q = 0;
-        for (; q + 3 < parts; q += 4) {
-            a0 += p[(long)q * stride]; a1 += p[(long)(q + 1) * stride]; a2 += p[(long)(q + 2) * stride]; a3 += p[(long)(q + 3) * stride];
-        }
-        for (; q < parts; ++q) a0 += p[(long)q * stride];
-        s.out[k][e] = (a0 + a1) + (a2 + a3);
+        float a = 0.f;
+        for (int q = lane; q < parts; q += 32) a += p[(long)q * stride];
+        a = warp_sum(a);
+        if (lane == 0) s.out[k][e] = a;
     }
 }
 }  // namespace sm
@@ -733,21 +768,38 @@ extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, c
     if (!ins || !outs || !numel || !parts || n <= 0) return -1;
     if (n > 8) return -2;
     gptst::sm::SumSegs s;
+    bool vec = true;
+    int maxparts = 0;
+    for (int k = 0; k < n; ++k) {
+        if (!ins[k] || !outs[k] || numel[k] <= 0 || parts[k] <= 0) return -1;
+        if (numel[k] % 4 != 0 || ((uintptr_t)ins[k] & 15) != 0 || ((uintptr_t)outs[k] & 15) != 0) vec = false;
+        if (parts[k] > maxparts) maxparts = parts[k];
+    }
+    long raw = 0;
+    for (int k = 0; k < n; ++k) raw += numel[k];
+    const bool warp_path = raw <= 16384 && maxparts >= 64;
+    if (warp_path) vec = false;
     long tot = 0;
     for (int k = 0; k < 8; ++k) {
         s.start[k] = tot;
         if (k < n) {
-            if (!ins[k] || !outs[k] || numel[k] <= 0 || parts[k] <= 0) return -1;
-            s.in[k] = ins[k]; s.out[k] = outs[k]; s.numel[k] = numel[k]; s.parts[k] = parts[k];
-            tot += numel[k];
+            s.in[k] = ins[k]; s.out[k] = outs[k]; s.numel[k] = vec ? numel[k] / 4 : numel[k]; s.parts[k] = parts[k];
+            tot += s.numel[k];
         } else { s.in[k] = nullptr; s.out[k] = nullptr; s.numel[k] = 0; s.parts[k] = 0; }
     }
     s.start[8] = tot;
     for (int k = n; k < 9; ++k) s.start[k] = tot;
     s.n = n;
+    if (warp_path) {
+        long blocks = (tot + 7) / 8;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        gptst::sm::sum_partials_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+        return (int)cudaGetLastError();
+    }
     long blocks = (tot + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gptst::sm::sum_partials_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+    if (vec) gptst::sm::sum_partials_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+    else gptst::sm::sum_partials_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
     return (int)cudaGetLastError();
 }
 

@@ -135,8 +135,8 @@ def tmix(x, M, out=None, *, transpose=False, accumulate=False):
     return out
 
 
-def tmix_bwd(dy, x, M, dx_io, prec):
-    """Fused backward of the mix (D = 64): dx_io += M^T o dy (in place) and returns dM."""
+def tmix_bwd(dy, x, M, dx_io, prec, raw=False):
+    """Fused backward of the mix (D = 64): dx_io += M^T o dy (in place) and returns dM (raw: its (splits, N, T, T) partials)."""
     B, T, N, D = x.shape
     dy, x, M = _c(dy), _c(x), _c(M)
     _chk(dy, x, M, dx_io)
@@ -145,10 +145,12 @@ def tmix_bwd(dy, x, M, dx_io, prec):
     part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
     rc = L.gptst_tmix_bwd(_p(dy), _p(x), _p(M), _p(dx_io), _p(part), B, T, N, D, prec, splits, _stream())
     _lib.check(rc, "gptst_tmix_bwd")
+    if raw:
+        return part
     return part[0] if splits == 1 else part.sum(0)
 
 
-def tmix_dM(dy, x):
+def tmix_dM(dy, x, raw=False):
     B, T, N, D = x.shape
     dy, x = _c(dy), _c(x)
     _chk(dy, x)
@@ -157,7 +159,40 @@ def tmix_dM(dy, x):
     part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
     rc = L.gptst_tmix_dM(_p(dy), _p(x), _p(part), B, T, N, D, splits, _stream())
     _lib.check(rc, "gptst_tmix_dM")
+    if raw:
+        return part
     return part[0] if splits == 1 else part.sum(0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Deferred partial sums.  The backward kernels write per-CTA / per-split partials of the parameter-side gradients
+# (dM_n, dW_n, db_n, ddyn, dWp, dbp).  Summing them at the tail of the block's backward put ~150 us of reductions on the
+# main chain of a PEMS08 step although nothing on that chain reads the sums.  Instead the block takes those inputs
+# EXPANDED to (P, *shape) (a stride-0 view, `expand_partials`) and returns the raw (P, *shape) partials as their
+# gradient; the reduction then is the expand's own backward, which autograd runs on the stream the expand was made on --
+# the block's table stream when `cap.tables` / `hyperTem.tables` (GPTST.py of this package) made it in the prologue.
+# ---------------------------------------------------------------------------------------------------
+def expand_partials(t, P: int):
+    """(shape) -> (P, *shape) stride-0 view whose backward sums the P gradient partials (torch's own expand)."""
+    return t.unsqueeze(0).expand((P,) + tuple(t.shape))
+
+
+def hypertem_partial_count(B: int, N: int, D: int) -> int:
+    """Number of dM_n partials the hyperTem backward writes for this geometry."""
+    L = _lib.lib()
+    return int(L.gptst_tmix_bwd_splits(B, N) if D == 64 else L.gptst_tmix_dM_splits(B, N))
+
+
+def cap_partial_counts(B: int, T: int, N: int, D: int, H: int):
+    """(P of dW_n / db_n, P of ddyn, P of dWp / dbp) the cap backward writes for this geometry."""
+    L = _lib.lib()
+    p_wn = int(L.gptst_gproj_splits(N, B * T, D))
+    p_dyn = int(L.gptst_cap_hop_bwd_parts(D))
+    if L.gptst_cap_route2_supported(N, D, H):
+        p_wp = int(L.gptst_linear_bwd_acc_splits(B * T * N, D))
+    else:
+        p_wp = int(L.gptst_cap_route_bwd_parts(B, T, N, D, H))
+    return p_wn, p_dyn, p_wp
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -165,8 +200,12 @@ def tmix_dM(dy, x):
 # ---------------------------------------------------------------------------------------------------
 class _HyperTemCore(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eb, Mn, W, bias, prec):
-        eb, Mn, W, bias = eb.contiguous(), Mn.contiguous(), W.contiguous(), bias.contiguous()
+    def forward(ctx, eb, Mn_e, W, bias, prec):
+        eb, W, bias = eb.contiguous(), W.contiguous(), bias.contiguous()
+        B, T, N, D = eb.shape
+        if Mn_e.dim() != 4 or Mn_e.shape[0] != hypertem_partial_count(B, N, D):
+            raise RuntimeError("hypertem_core: Mn must be expanded to (hypertem_partial_count(B, N, D), N, T, T)")
+        Mn = Mn_e[0].contiguous()
         ret = tmix(eb, Mn)
         out = gproj_fwd(ret, W, bias, eb, node_grouped=False, act=True, prec=prec)
         ctx.save_for_backward(eb, Mn, W, ret, out)
@@ -180,15 +219,19 @@ class _HyperTemCore(torch.autograd.Function):
         dret, dW, db, deb = gproj_bwd(dout, out, ret, W, node_grouped=False, act=True, prec=ctx.prec, want_dres=True)
         B, T, N, D = eb.shape
         if D == 64:
-            dM = tmix_bwd(dret, eb, Mn, deb, ctx.prec)
+            dM_part = tmix_bwd(dret, eb, Mn, deb, ctx.prec, raw=True)
         else:
             tmix(dret, Mn, deb, transpose=True, accumulate=True)
-            dM = tmix_dM(dret, eb)
-        return deb, dM, dW.view(B, T, D, D), db.view(B, T, D), None
+            dM_part = tmix_dM(dret, eb, raw=True)
+        return deb, dM_part, dW.view(B, T, D, D), db.view(B, T, D), None
 
 
 def hypertem_core(eb, Mn, W, bias, prec=None):
-    """eb (B,T,N,D); Mn (N,T,T) = A_n^T A_n; W (B,T,D,D); bias (B,T,D)."""
+    """eb (B,T,N,D); Mn (N,T,T) = A_n^T A_n, or already expanded to (P,N,T,T) by `expand_partials`; W (B,T,D,D); bias (B,T,D)."""
+    if Mn.dim() == 3:
+        if not eb.is_cuda:
+            raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
+        Mn = expand_partials(Mn, hypertem_partial_count(eb.shape[0], eb.shape[2], eb.shape[3]))
     return _HyperTemCore.apply(eb, Mn, W, bias, default_precision() if prec is None else prec)
 
 
@@ -197,11 +240,15 @@ def hypertem_core(eb, Mn, W, bias, prec=None):
 # ---------------------------------------------------------------------------------------------------
 class _CapCore(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec):
-        x, Wp, bp, dadj, dyn, Wn, bn = (t.contiguous() for t in (x, Wp, bp, dadj, dyn, Wn, bn))
-        _chk(x, Wp, bp, dadj, dyn, Wn, bn)
+    def forward(ctx, x, Wp_e, bp_e, dadj, dyn_e, Wn_e, bn_e, num_route, prec):
+        x, dadj = x.contiguous(), dadj.contiguous()
         B, T, N, D = x.shape
-        H, HT = dadj.shape[2], dyn.shape[1]
+        H, HT = dadj.shape[2], dyn_e.shape[2]
+        p_wn, p_dyn, p_wp = cap_partial_counts(B, T, N, D, H)
+        if (Wp_e.shape[0], bp_e.shape[0], dyn_e.shape[0], Wn_e.shape[0], bn_e.shape[0]) != (p_wp, p_wp, p_dyn, p_wn, p_wn):
+            raise RuntimeError("cap_core: parameter-side inputs must be expanded by cap_partial_counts(B, T, N, D, H)")
+        Wp, bp, dyn, Wn, bn = (t[0].contiguous() for t in (Wp_e, bp_e, dyn_e, Wn_e, bn_e))
+        _chk(x, Wp, bp, dadj, dyn, Wn, bn)
         L = _lib.lib()
         st = _stream()
         _count(2)  # route_fwd + hop_e1 + recon_hop share `st`
@@ -212,9 +259,16 @@ class _CapCore(torch.autograd.Function):
         v = torch.empty_like(s)
         e1 = torch.empty((B, HT, D), device=x.device, dtype=torch.float32)
         recon = torch.empty_like(x)
-        _lib.check(L.gptst_cap_hop_e1(_p(s), _p(dyn), _p(e1), B, T, D, H, HT, st), "gptst_cap_hop_e1")
-        _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
-                   "gptst_cap_recon_hop")
+        if os.environ.get("GPTST_B200_HOP", "split") == "fused":
+            # opt-in A/B variant: hop_e1 folded into recon_hop (one launch).  Measured SLOWER on the B200 (80 us vs 6.5 + 22 us:
+            # every slab CTA recomputes its sample's E1 out of L2), so the split pair stays the default.
+            _count(-1)
+            _lib.check(L.gptst_cap_recon_hop_fused(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
+                       "gptst_cap_recon_hop_fused")
+        else:
+            _lib.check(L.gptst_cap_hop_e1(_p(s), _p(dyn), _p(e1), B, T, D, H, HT, st), "gptst_cap_hop_e1")
+            _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
+                       "gptst_cap_recon_hop")
         out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
         ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1)
         ctx.prec = prec
@@ -267,14 +321,26 @@ class _CapCore(torch.autograd.Function):
             dbp_part = torch.empty((parts, D), device=x.device, dtype=torch.float32)
             _lib.check(L.gptst_cap_route_bwd(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dx), _p(ddadj), _p(dWp_part),
                                              _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
-        # the five partial buffers of this backward are summed by one launch
-        dWn, dbn, ddyn, dWp, dbp = sum_partials(dWn_part, dbn_part, ddyn_part, dWp_part, dbp_part)
-        return dx, dWp, dbp, ddadj, ddyn, dWn, dbn, None, None
+        # the five partial buffers leave as they are: they are the gradients of the EXPANDED inputs, summed by the expands' own
+        # backward on the stream that made them (see `expand_partials`)
+        return dx, dWp_part, dbp_part, ddadj, ddyn_part, dWn_part, dbn_part, None, None
 
 
-def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None):
-    """x (B,T,N,D); Wp (D,D) [out,in]; dadj (B,T,H,N); dyn (B,HT,T*H); Wn (N,D,D); bn (N,D).
-    Returns (out (B,T,N,D), c (B,T,H,N) non-differentiable)."""
+def cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, H):
+    """The five parameter-side inputs of `cap_core` expanded for this geometry (call it where those tensors are produced)."""
+    p_wn, p_dyn, p_wp = cap_partial_counts(B, T, N, D, H)
+    return (expand_partials(Wp, p_wp), expand_partials(bp, p_wp), expand_partials(dyn, p_dyn), expand_partials(Wn, p_wn),
+            expand_partials(bn, p_wn))
+
+
+def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None, expanded=False):
+    """x (B,T,N,D); Wp (D,D) [out,in]; dadj (B,T,H,N); dyn (B,HT,T*H); Wn (N,D,D); bn (N,D) -- or, with expanded=True, Wp, bp,
+    dyn, Wn, bn as returned by `cap_expand`.  Returns (out (B,T,N,D), c (B,T,H,N) non-differentiable)."""
+    if not expanded:
+        if not x.is_cuda:
+            raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
+        B, T, N, D = x.shape
+        Wp, bp, dyn, Wn, bn = cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, dadj.shape[2])
     return _CapCore.apply(x, Wp, bp, dadj, dyn, Wn, bn, num_route, default_precision() if prec is None else prec)
 
 
@@ -524,6 +590,42 @@ class _Affine1(torch.autograd.Function):
 
 def affine1(x, weight, bias):
     return _Affine1.apply(x, weight, bias)
+
+
+class _ProjOut(torch.autograd.Function):
+    """y = x W^T + b for nn.Linear(D, O) with O <= 4 outputs (decoder.dim_flow_out, GPTST.py:454-458): one streaming pass over x
+    forward, one backward (dX written, dW / db as per-CTA partials) instead of a GEMV and three library GEMM / reduce kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight, bias = x.contiguous(), weight.contiguous(), bias.contiguous()
+        _chk(x, weight, bias)
+        O, D = weight.shape
+        rows = x.numel() // D
+        y = torch.empty(x.shape[:-1] + (O,), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gptst_proj_out_fwd(_p(x), _p(weight), _p(bias), _p(y), rows, D, O, _stream()), "gptst_proj_out_fwd")
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        _chk(dy)
+        O, D = weight.shape
+        rows = x.numel() // D
+        L = _lib.lib()
+        parts = L.gptst_proj_out_bwd_parts(rows)
+        part = torch.empty((parts, O * D + O), device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        _lib.check(L.gptst_proj_out_bwd(_p(dy), _p(x), _p(weight), _p(dx), _p(part), rows, D, O, parts, _stream()), "gptst_proj_out_bwd")
+        (tot,) = sum_partials(part)
+        return dx, tot[:O * D].view(O, D), tot[O * D:]
+
+
+def proj_out(x, weight, bias):
+    """(..., D) -> (..., O): nn.Linear with O <= 4 output features through the sm_100a streaming kernels (D = 64 or 128)."""
+    return _ProjOut.apply(x, weight, bias)
 
 
 # ---------------------------------------------------------------------------------------------------

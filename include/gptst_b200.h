@@ -73,6 +73,10 @@ int gptst_cap_recon(const float* c, const float* v, float* recon, int B, int T, 
 int gptst_cap_hop_e1(const float* s, const float* dyn, float* e1, int B, int T, int D, int H, int HT, void* stream);
 int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const float* e1, float* v, float* recon, int B,
                         int T, int N, int D, int H, int HT, void* stream);
+/* recon_hop with hop_e1 folded in (every slab CTA recomputes its sample's E1 from s, 123k MACs): e1 is an OUTPUT here, kept for
+ * the backward pass.  Opt-in (GPTST_B200_HOP=fused): measured slower than the split pair on the B200 (80 us vs 6.5 + 22 us).   */
+int gptst_cap_recon_hop_fused(const float* c, const float* s, const float* dyn, float* e1, float* v, float* recon, int B, int T,
+                              int N, int D, int H, int HT, void* stream);
 /* ---- cap backward pieces ------------------------------------------------------
  * dv = c drecon, dcr = v drecon^T                                                                            */
 int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int B, int T, int N,
@@ -174,6 +178,14 @@ int gptst_sum_partials(const float* const* ins, float* const* outs, const long* 
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
+/* decoder output projection dim_flow_out = nn.Linear(D, O), O = input_base_dim <= 4 (GPTST.py:454-458), replacing
+ * `self.dim_flow_out(flow_decode)` and its autograd: y (rows,O) = x (rows,D) W^T + b, W (O,D) as nn.Linear stores it, D = 64|128.
+ * Backward in one pass: dX (rows,D) = dy W (may be NULL) and part (parts, O*D + O) = per-CTA partials of dW = dy^T x
+ * ([p][o*D + d]) and db = sum dy ([p][O*D + o]), parts = gptst_proj_out_bwd_parts(rows), summed by the caller.              */
+int gptst_proj_out_fwd(const float* x, const float* W, const float* b, float* y, long rows, int D, int O, void* stream);
+int gptst_proj_out_bwd_parts(long rows);
+int gptst_proj_out_bwd(const float* dy, const float* x, const float* W, float* dX, float* part, long rows, int D, int O,
+                       int parts, void* stream);
 
 /* ---- fused pre-training loss + analytic gradients ------------------------------------
  * mode 0: probe loss mean|(o - x)*m| ; mode 1: masked MAE of Run.py:91-101 / lib/metrics.py:11-18 (inverse z-score with

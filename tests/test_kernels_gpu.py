@@ -453,3 +453,82 @@ def test_eval_glue_fusion_matches_reference_formula(prec):
     check(xc.grad, x.grad, 2e-4, "fusion dx")
     for k, p in glue.named_parameters():
         check(p.grad, P[k].grad, 2e-4, "fusion grad " + k)
+
+
+@pytest.mark.parametrize("rows_shape,D,O", [((3, 12, 37), 64, 1), ((2, 12, 170), 64, 2), ((1, 5, 7), 128, 4), ((64, 12, 170), 64, 1)])
+def test_proj_out_matches_linear(rows_shape, D, O):
+    """decoder.dim_flow_out (GPTST.py:454-458) through gptst_proj_out_fwd / _bwd vs nn.Linear in fp64."""
+    from gptst_b200 import ops
+    lin = torch.nn.Linear(D, O).double()
+    x = rnd(*rows_shape, D, seed=11).requires_grad_()
+    want = lin(x)
+    g = rnd(*rows_shape, O, seed=12)
+    want.backward(g)
+    xc = x.detach().float().cuda().requires_grad_()
+    w, b = lin.weight.detach().float().cuda().requires_grad_(), lin.bias.detach().float().cuda().requires_grad_()
+    got = ops.proj_out(xc, w, b)
+    assert got.shape == want.shape
+    check(got, want.detach(), 2e-6, "proj_out y")
+    got.backward(g.float().cuda())
+    check(xc.grad, x.grad, 2e-6, "proj_out dx")
+    check(w.grad, lin.weight.grad, 2e-5, "proj_out dW")
+    check(b.grad, lin.bias.grad, 2e-5, "proj_out db")
+    # weights only (dX = NULL)
+    w2 = w.detach().clone().requires_grad_()
+    ops.proj_out(xc.detach(), w2, b.detach()).backward(g.float().cuda())
+    assert torch.equal(w2.grad, w.grad)
+
+
+@pytest.mark.parametrize("shapes", [[(3, 170, 64, 64), (3, 170, 64), (4, 64, 16, 120), (7, 64, 64), (7, 64)],   # float4 path
+                                    [(510, 650)],                                                           # warp-per-element path
+                                    [(296, 65), (5, 33, 3)],                                                # warp path, odd sizes
+                                    [(3, 1001), (1, 8), (2, 4096)]])                                        # scalar path + a P = 1 view
+def test_sum_partials_paths(shapes):
+    from gptst_b200 import ops
+    parts = [rnd(*s, seed=20 + i).float().cuda() for i, s in enumerate(shapes)]
+    got = ops.sum_partials(*parts)
+    for p, o in zip(parts, got):
+        check(o, p.double().sum(0).cpu(), 2e-6, "sum_partials")
+    again = ops.sum_partials(*parts)
+    assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+
+def test_deferred_partial_sums_through_tables():
+    """`cap.tables` / `hyperTem.tables` hand the blocks stride-0 expanded parameter-side inputs; the blocks return raw gradient
+    partials and the expands' backward sums them.  Same gradients as the plain-tensor entry points (which expand internally)."""
+    import types
+    from gptst_b200 import GPTST as G, ops
+    torch.manual_seed(3)
+    B, T, N, D, d, ds, H, HT, Ht = 2, 12, 41, 64, 16, 4, 10, 16, 8
+    capm = G.cap(D, N, T, d, ds, H, HT, 2).cuda()
+    htm = G.hyperTem(T, N, D, D, d, Ht).cuda()
+    for p in list(capm.parameters()) + list(htm.parameters()):
+        torch.nn.init.uniform_(p.data, -0.3, 0.3)
+    E = (torch.rand(N, d, device="cuda") - 0.5).requires_grad_()
+    time_eb = (torch.rand(B, T, d, device="cuda") - 0.5).requires_grad_()
+    teb = (torch.rand(B, T, ds, device="cuda") - 0.5).requires_grad_()
+    spg = (torch.rand(B, ds, device="cuda") - 0.5).requires_grad_()
+    x = torch.randn(B, T, N, D, device="cuda").requires_grad_()
+    go = torch.randn(B, T, N, D, device="cuda")
+    leaves = [x, E, time_eb, teb, spg] + list(capm.parameters()) + list(htm.parameters())
+
+    def run(through_tables):
+        for t in leaves:
+            t.grad = None
+        if through_tables:
+            y = htm(x, E, time_eb)
+            y, _, _ = capm(y, E, spg, teb)
+        else:
+            A = ops.lowrank_table(E, htm.adj)
+            y = ops.hypertem_core(x, ops.mix_matrix(A), ops.lowrank_table(time_eb, htm.weights_pool), ops.lowrank_table(time_eb, htm.bias_pool))
+            y, _ = ops.cap_core(y, capm.ln_p.weight, capm.ln_p.bias, ops.lowrank_table(teb, capm.adj), ops.lowrank_table(spg, capm.t_adj),
+                                ops.lowrank_table(E, capm.weights_spa), ops.lowrank_table(E, capm.bias_spa), 2)
+        y.backward(go)
+        return y.detach().clone(), [t.grad.clone() for t in leaves]
+
+    ya, ga = run(True)
+    yb, gb = run(False)
+    assert torch.equal(ya, yb)
+    for a, b in zip(ga, gb):
+        assert a.shape == b.shape
+        assert_close(a, b.double().cpu(), atol=scale_tol(b, 1e-6), rtol=0.0, what="deferred partial sums")
