@@ -165,6 +165,15 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
     float* dXg = dX + (long)grp * gs;
     float* dRg = dRes ? dRes + (long)grp * gs : nullptr;
 
+    // the first chunk's dY / X rows start streaming in before the weight tile is fetched and converted (two cp.async groups,
+    // consumed in the chunk loop below): the weight's global latency used to sit in front of them
+    if (split * cps * NW * 16 < R) {
+        const int r0 = split * cps * NW * 16 + n0;
+        stage16(Gs + (size_t)n0 * ROWB, dYg, rs, r0, R, lane);
+        cp_async_commit();
+        stage16(Xs + (size_t)n0 * ROWB, Xg, rs, r0, R, lane);
+        cp_async_commit();
+    }
     const float* Wg = W + (size_t)grp * D * D;
     {   // issue all W_g loads of this thread first, convert afterwards
         constexpr int WI = (D * 16 + NT - 1) / NT;
@@ -206,10 +215,12 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
         unsigned char* Gw = Gs + (size_t)n0 * ROWB;
         // dY first, X second (two cp.async groups): the dy conversion and the dX product only need dY, so the X rows
         // keep streaming in underneath them; Y goes straight to registers so its latency overlaps the staging as well
-        stage16(Gw, dYg, rs, r0, R, lane);
-        cp_async_commit();
-        stage16(Xw, Xg, rs, r0, R, lane);
-        cp_async_commit();
+        if (it > 0) {                                             // chunk 0 was issued ahead of the weight staging
+            stage16(Gw, dYg, rs, r0, R, lane);
+            cp_async_commit();
+            stage16(Xw, Xg, rs, r0, R, lane);
+            cp_async_commit();
+        }
         constexpr bool PREY = NW * 32 * MINB <= 512;   // room for 32 more live registers (cap >= 128 per thread)
         float4 yv[PREY ? 8 : 1];
         if (PREY && act) {

@@ -172,9 +172,36 @@ def tmix_dM(dy, x, raw=False):
 # gradient; the reduction then is the expand's own backward, which autograd runs on the stream the expand was made on --
 # the block's table stream when `cap.tables` / `hyperTem.tables` (GPTST.py of this package) made it in the prologue.
 # ---------------------------------------------------------------------------------------------------
+class _ExpandPartials(torch.autograd.Function):
+    """(shape) -> (P, *shape) stride-0 views of several tensors at once; the backward sums the P gradient partials of all of them
+    with ONE gptst_sum_partials launch (fixed order, deterministic) on the stream this node's forward ran on."""
+
+    @staticmethod
+    def forward(ctx, counts, *ts):
+        ctx.set_materialize_grads(False)
+        return tuple(t.unsqueeze(0).expand((int(p),) + tuple(t.shape)) for t, p in zip(ts, counts))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        idx = [i for i, g in enumerate(gs) if g is not None]
+        sums = sum_partials(*[gs[i] for i in idx]) if idx else ()
+        out = [None] * len(gs)
+        for i, s in zip(idx, sums):
+            out[i] = s
+        return (None, *out)
+
+
+def expand_partials_many(ts, counts):
+    """Stride-0 (P_i, *shape_i) views of the CUDA tensors `ts`; gradients arriving as (P_i, *shape_i) partials are summed by the
+    views' backward (one launch for all of them; GPTST_B200_EXPAND=native uses torch's own expand / sum_to_size instead)."""
+    if os.environ.get("GPTST_B200_EXPAND", "fused") == "native":
+        return tuple(t.unsqueeze(0).expand((int(p),) + tuple(t.shape)) for t, p in zip(ts, counts))
+    return _ExpandPartials.apply(tuple(int(p) for p in counts), *ts)
+
+
 def expand_partials(t, P: int):
-    """(shape) -> (P, *shape) stride-0 view whose backward sums the P gradient partials (torch's own expand)."""
-    return t.unsqueeze(0).expand((P,) + tuple(t.shape))
+    """(shape) -> (P, *shape) stride-0 view whose backward sums the P gradient partials."""
+    return expand_partials_many((t,), (P,))[0]
 
 
 def hypertem_partial_count(B: int, N: int, D: int) -> int:
@@ -329,8 +356,7 @@ class _CapCore(torch.autograd.Function):
 def cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, H):
     """The five parameter-side inputs of `cap_core` expanded for this geometry (call it where those tensors are produced)."""
     p_wn, p_dyn, p_wp = cap_partial_counts(B, T, N, D, H)
-    return (expand_partials(Wp, p_wp), expand_partials(bp, p_wp), expand_partials(dyn, p_dyn), expand_partials(Wn, p_wn),
-            expand_partials(bn, p_wn))
+    return expand_partials_many((Wp, bp, dyn, Wn, bn), (p_wp, p_wp, p_dyn, p_wn, p_wn))
 
 
 def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None, expanded=False):
@@ -583,7 +609,7 @@ class _Affine1(torch.autograd.Function):
         parts = L.gptst_affine1_bwd_parts(n)
         part = torch.empty((parts, 2, D), device=dy.device, dtype=torch.float32)
         _lib.check(L.gptst_affine1_bwd(_p(dy), _p(x.contiguous()), _p(part), n, D, parts, _stream()), "gptst_affine1_bwd")
-        tot = part.sum(0)
+        (tot,) = sum_partials(part)
         dx = (dy * weight.view(-1)).sum(-1, keepdim=True) if ctx.needs_input_grad[0] else None
         return dx, tot[0].view_as(weight), tot[1]
 
