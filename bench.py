@@ -390,6 +390,11 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        if args.no_rooflines:      # A/B runs: step throughput only
+            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "e2e": value_e2e, "e2e_ms_per_step": ms_e2e / args.steps,
+                              "last_loss": last_loss, "gpu_launches": launches, "clocks": clocks,
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("GPTST_B200_")}}), flush=True)
+            return 0
         peak, peak_src = measured_peak()
         algo, cap_ms = cap_forward_roofline(N, D, B)
         ht_algo, ht_ms = hypertem_forward_time(N, D, B)
@@ -447,6 +452,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--epoch", type=int, default=200, help="epoch argument passed to the model (mask phase)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rooflines", action="store_true", help="A/B runs: print only the step numbers (not a bench line)")
     ap.add_argument("--eager", action="store_true", help="time the eager step (what an unmodified Run.py loop launches) instead of the graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -512,10 +512,13 @@ class GPTST_Model(nn.Module):
         dev = source.device
         key = (dev.index, main.cuda_stream)
         if self._streams is None or self._streams[0] != key:
-            self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(9)], [torch.cuda.Stream(device=dev) for _ in range(9)],
-                             torch.cuda.Stream(device=dev, priority=-1), [torch.cuda.Stream(device=dev, priority=-1) for _ in range(2)])
             # the scorer (and its two table streams) is on the critical front of the adaptive phase -- the encoder cannot start
-            # before the mask exists -- so it gets the priority of the main chain; the STHCN prologues keep the default (lowest)
+            # before the mask exists -- so it gets the priority of the main chain; the STHCN prologues keep the default (lowest).
+            # Autograd replays the scorer's backward (KL branch) on the same streams, where it is NOT critical but competes with
+            # the head of the main backward chain: GPTST_B200_SCORER_PRIO=low is the A/B knob for that trade.
+            sp = 0 if os.environ.get("GPTST_B200_SCORER_PRIO", "high") == "low" else -1
+            self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(9)], [torch.cuda.Stream(device=dev) for _ in range(9)],
+                             torch.cuda.Stream(device=dev, priority=sp), [torch.cuda.Stream(device=dev, priority=sp) for _ in range(2)])
         fork = torch.cuda.Event()
         fork.record(main)
         out = []

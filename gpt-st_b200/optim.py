@@ -7,6 +7,7 @@ travels through a pinned host buffer (a memcpy node that re-reads the same, stil
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, Optional
 
 import torch
@@ -33,6 +34,7 @@ class FusedAdamClip:
         self._tables = {}                                  # key -> [pinned table, dev table, dev block map, partial, nblocks, pinned map]
         self._captures = 0
         self.chunk = _lib.lib().gptst_opt_chunk()
+        self._pre = None                                   # buffers of prefetch_tables() waiting for step()
 
     def set_lr(self, lr: float) -> None:
         self.hyper[0:1].fill_(lr)
@@ -76,11 +78,63 @@ class FusedAdamClip:
         ent[1].copy_(ent[0], non_blocking=True)
         return ent
 
+    def prefetch_tables(self) -> None:
+        """Call at the START of a step that is being captured into a CUDA graph (opt-in, GPTST_B200_OPT_PREFETCH=1): issues the
+        two pinned -> device table copies on a forked stream right away, so that their memcpy nodes hang off the root of the
+        graph instead of sitting between the last gradient kernel and the optimiser.  The pinned buffers are filled by
+        `step()` later in the same capture -- a memcpy node reads its source when the graph is replayed, not when it is
+        captured.  Outside a capture (or when disabled) this is a no-op and `step()` builds the tables as before."""
+        self._pre = None
+        if os.environ.get("GPTST_B200_OPT_PREFETCH", "0") != "1" or not torch.cuda.is_current_stream_capturing():
+            return
+        nblocks = sum((p.numel() + self.chunk - 1) // self.chunk for p in self.params)
+        pinned = torch.zeros((len(self.params), 6), dtype=torch.int64).pin_memory()
+        bpin = torch.zeros((nblocks, 2), dtype=torch.int32).pin_memory()
+        tdev = torch.empty((len(self.params), 6), dtype=torch.int64, device=self.device)
+        bdev = torch.empty((nblocks, 2), dtype=torch.int32, device=self.device)
+        part = torch.empty(nblocks, dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            tdev.copy_(pinned, non_blocking=True)
+            bdev.copy_(bpin, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        self._pre = (pinned, bpin, tdev, bdev, part, ev, side)
+
+    def _table_prefetched(self, live):
+        """Fill the pinned buffers of `prefetch_tables` for the gradients that exist now and join its stream."""
+        pinned, bpin, tdev, bdev, part, ev, _side = self._pre
+        rows, bmap = [], []
+        for idx, p in enumerate(live):
+            if p not in self.state:
+                self.state[p] = (torch.zeros_like(p, memory_format=torch.contiguous_format),
+                                 torch.zeros_like(p, memory_format=torch.contiguous_format), self.host_steps)
+            m, v, first = self.state[p]
+            g = p.grad
+            if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
+                raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
+            n = p.numel()
+            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, first])
+            bmap += [[idx, c] for c in range((n + self.chunk - 1) // self.chunk)]
+        pinned[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))          # host writes: the captured copies read them at replay
+        bpin[:len(bmap)].copy_(torch.tensor(bmap, dtype=torch.int32))
+        torch.cuda.current_stream().wait_event(ev)                                # join the forked branch
+        self._captures += 1
+        self._tables[("prefetched", self._captures)] = self._pre                 # the graph owns these buffers
+        self._pre = None
+        return [pinned, tdev, bdev, part, len(bmap), bpin]
+
     def step(self) -> None:
         live = [p for p in self.params if p.grad is not None]
+        pre = getattr(self, "_pre", None)
         if not live:
+            if pre is not None:
+                torch.cuda.current_stream().wait_event(pre[5])
+                self._pre = None
             return
-        ent = self._table(live)
+        ent = self._table_prefetched(live) if pre is not None else self._table(live)
         self.host_steps += 1
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream

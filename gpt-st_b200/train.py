@@ -68,6 +68,8 @@ class PretrainStep:
 
     def _body(self, src, epoch):
         self._zero_grad()
+        if self.fused_opt is not None:
+            self.fused_opt.prefetch_tables()           # no-op unless capturing with GPTST_B200_OPT_PREFETCH=1
         outs = self.model(src, src, None, epoch)
         loss = self.loss_fn(outs, src, epoch)
         loss.backward()
