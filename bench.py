@@ -354,6 +354,8 @@ def run_ours(args):
         barrier()
         l0, r0 = ops.launch_count(), stepper.replays
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_range and not e2e:
+            torch.cuda.profiler.start()     # `ncu --profile-from-start off` then profiles exactly the timed graph replays
         e0.record()
         last = None
         for i in range(nsteps):
@@ -364,6 +366,8 @@ def run_ours(args):
                 last = stepper(resident[i % nbuf], epoch)
         e1.record()
         torch.cuda.synchronize()
+        if args.profiler_range and not e2e:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         barrier()
         if world > 1:
@@ -452,6 +456,10 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--epoch", type=int, default=200, help="epoch argument passed to the model (mask phase)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed (resident-input) steps with cudaProfilerStart/Stop: `ncu --profile-from-start off "
+                         "--metrics gpu__time_duration.sum ... python bench.py --steps 2 --warmup 1 --profiler-range --no-rooflines "
+                         "--no-cpu-baseline` lists exactly the kernels of the timed graph replays (never a bench value)")
     ap.add_argument("--no-rooflines", action="store_true", help="A/B runs: print only the step numbers (not a bench line)")
     ap.add_argument("--eager", action="store_true", help="time the eager step (what an unmodified Run.py loop launches) instead of the graph")
     args = ap.parse_args()

@@ -12,8 +12,8 @@ timeout 70 python bench.py > $O/bench_v.json 2> $O/bench_v.err
 el "bench default"
 timeout 50 python tools/ab_knobs.py > $O/ab_knobs.jsonl 2> $O/ab_knobs.err
 el "ab knobs"
-timeout 45 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2400 --launch-count 900 --csv --log-file $O/launches_r01_graph.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-rooflines > $O/ncu_list.log 2>&1
+timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/launches_graph.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-rooflines --profiler-range > $O/ncu_list.log 2>&1
 el "ncu list"
 timeout 25 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
 el "smoke: $(tail -1 $O/smoke.log | cut -c1-120)"
