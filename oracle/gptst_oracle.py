@@ -343,6 +343,48 @@ def synthetic_loss(outs, source: Tensor, epoch: int, change_epoch: int = 10) -> 
 # ----------------------------------------------------------------------------------------
 # parameter construction with the reference's names / shapes / registration order (§8b)
 # ----------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------
+# eval path: the gate of Enhance_model and STGCN's gated temporal convolution
+# ---------------------------------------------------------------------------------------------------
+def fusion_gate(flow_eb: Tensor, time_eb: Tensor, P: Dict[str, Tensor], pre: str = "") -> Tensor:
+    """reference model/Model.py:12-18 (Fusion.forward): z = sigmoid(HS_fc(x) + HT_fc(y)); output_fc(z x + (1 - z) y)."""
+    z = torch.sigmoid(linear(flow_eb, P[pre + "HS_fc.weight"], P[pre + "HS_fc.bias"]) +
+                      linear(time_eb, P[pre + "HT_fc.weight"], P[pre + "HT_fc.bias"]))
+    h = z * flow_eb + (1 - z) * time_eb
+    return linear(h, P[pre + "output_fc.weight"], P[pre + "output_fc.bias"])
+
+
+def eval_glue(source: Tensor, x_pre: Tensor, P: Dict[str, Tensor], ibd: int) -> Tensor:
+    """reference model/Model.py:106-109: lin_test on the raw flow channels, then the gate with the encoder output."""
+    x_t1 = linear(source[..., :ibd], P["lin_test.weight"], P["lin_test.bias"])
+    return fusion_gate(x_pre, x_t1, P, "fusion.")
+
+
+def temporal_conv_glu(x: Tensor, conv_w: Tensor, conv_b: Tensor, align_w: Optional[Tensor] = None,
+                      align_b: Optional[Tensor] = None) -> Tensor:
+    """reference model/STGCN/stgcn.py:10-53, TemporalConvLayer with act = "GLU" on x (B, c_in, T, N):
+    conv = Conv2d(c_in, 2 c_out, (kt, 1), padding (kt-1)//2) over the time axis; x_in = Align(x) (1x1 conv when c_in > c_out,
+    zero-padded channels when c_in < c_out); out = (conv[:, :c_out] + x_in) * sigmoid(conv[:, c_out:]).
+    Restated without nn.Conv2d: an explicit sum over the kt taps of shifted, zero-padded slices."""
+    B, c_in, T, N = x.shape
+    c2, _, kt, _ = conv_w.shape
+    c_out = c2 // 2
+    pad = (kt - 1) // 2
+    T_out = T + 2 * pad - kt + 1
+    xp = torch.zeros(B, c_in, T + 2 * pad, N, dtype=x.dtype)
+    xp[:, :, pad:pad + T] = x
+    conv = conv_b.view(1, c2, 1, 1).expand(B, c2, T_out, N).clone()
+    for k in range(kt):
+        conv = conv + torch.einsum("oi,bitn->botn", conv_w[:, :, k, 0], xp[:, :, k:k + T_out])
+    if c_in > c_out:
+        x_in = torch.einsum("oi,bitn->botn", align_w[:, :, 0, 0], x) + align_b.view(1, c_out, 1, 1)
+    elif c_in < c_out:
+        x_in = torch.cat([x, torch.zeros(B, c_out - c_in, T, N, dtype=x.dtype)], dim=1)
+    else:
+        x_in = x
+    return (conv[:, :c_out] + x_in) * torch.sigmoid(conv[:, c_out:])
+
+
 def param_shapes(cfg) -> "list[tuple[str, tuple]]":
     N, D, d, ds = cfg.num_nodes, cfg.hidden_dim, cfg.embed_dim, cfg.embed_dim_spa
     H, HT, Ht, T, ibd = cfg.HS, cfg.HT, cfg.HT_Tem, cfg.horizon, cfg.input_base_dim

@@ -13,6 +13,8 @@ oracle/ref_import.py; the reference ships no fixtures of its own)
   pems08_ckpt.npz      shipped PEMS08 checkpoint on the first 8 PEMS08 test windows: the input windows,
                        a strided sample + moments of the eval-mode encoder output, and the pretrain-mode
                        masked MAE / KL at epoch 1 and 300 (the SURVEY.md §8c numbers).
+  eval_path.npz        eval-path pieces next to the encoder: the reference ``Fusion`` gate + ``lin_test``
+                       and STGCN's ``TemporalConvLayer`` (GLU) in four channel / kernel configurations, with gradients.
 """
 from __future__ import annotations
 
@@ -226,6 +228,52 @@ def pems08(ref, root):
     print("pems08_ckpt.npz", sum(v.size for v in out.values()), "elements")
 
 
+def eval_path(root):
+    """Fusion (model/Model.py:5-18, class source extracted with ast: the module itself imports the whole predictor zoo) and
+    STGCN's TemporalConvLayer with GLU (model/STGCN/stgcn.py:25-53, imported as is) on seeded inputs, with all gradients."""
+    import ast
+    import importlib.util
+    src = open(os.path.join(root, "model", "Model.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "Fusion")
+    ns = {"torch": torch, "nn": torch.nn}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "Model.py:Fusion", "exec"), ns)
+    out = {}
+    torch.manual_seed(70)
+    D, ibd = 16, 1
+    fus = ns["Fusion"](D)
+    lin = torch.nn.Linear(ibd, D)
+    source = torch.randn(3, 12, 9, ibd + 2)
+    x_pre = torch.randn(3, 12, 9, D, requires_grad=True)
+    y = fus(x_pre, lin(source[..., :ibd]))                    # Model.py:106-109
+    g = torch.randn_like(y)
+    y.backward(g)
+    out.update({"glue.source": npd(source), "glue.x_pre": npd(x_pre), "glue.out": npd(y), "glue.gout": npd(g),
+                "glue.g.x_pre": npd(x_pre.grad), "glue.dims": np.array([D, ibd])})
+    for k, v in list(fus.named_parameters()) + [("lin_test." + k, v) for k, v in lin.named_parameters()]:
+        name = k if k.startswith("lin_test.") else "fusion." + k
+        out["glue.p." + name] = npd(v)
+        out["glue.g." + name] = npd(v.grad)
+    spec = importlib.util.spec_from_file_location("ref_stgcn", os.path.join(root, "model", "STGCN", "stgcn.py"))
+    st = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(st)
+    for tag, (kt, c_in, c_out, T) in {"same": (3, 8, 8, 12), "narrow": (3, 12, 6, 12), "widen": (3, 4, 8, 12), "wide_kernel": (5, 8, 8, 12)}.items():
+        torch.manual_seed(80 + kt + c_in)
+        layer = st.TemporalConvLayer(kt, c_in, c_out, "GLU")
+        x = torch.randn(2, c_in, T, 7, requires_grad=True)
+        y = layer(x)
+        g = torch.randn_like(y)
+        y.backward(g)
+        pre = f"glu.{tag}."
+        out.update({pre + "x": npd(x), pre + "out": npd(y), pre + "gout": npd(g), pre + "g.x": npd(x.grad),
+                    pre + "conv.weight": npd(layer.conv.weight), pre + "conv.bias": npd(layer.conv.bias),
+                    pre + "g.conv.weight": npd(layer.conv.weight.grad), pre + "g.conv.bias": npd(layer.conv.bias.grad)})
+        if c_in > c_out:
+            out.update({pre + "align.weight": npd(layer.align.conv1x1.weight), pre + "align.bias": npd(layer.align.conv1x1.bias),
+                        pre + "g.align.weight": npd(layer.align.conv1x1.weight.grad), pre + "g.align.bias": npd(layer.align.conv1x1.bias.grad)})
+    np.savez_compressed(os.path.join(GOLD, "eval_path.npz"), **out)
+    print("eval_path.npz", sum(v.size for v in out.values()), "elements")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     root = reference_root()
@@ -239,6 +287,7 @@ def main():
     model_case(ref, "pre_phase1_ibd2", small_cfg(input_base_dim=2), 2, 5, 50)
     model_case(ref, "pre_phase2_ibd2", small_cfg(input_base_dim=2), 2, 120, 60)
     pems08(ref, root)
+    eval_path(root)
 
 
 if __name__ == "__main__":

@@ -182,3 +182,43 @@ def test_pems08_checkpoint_golden():
         st = g[f"pre{ep}.stats"]
         assert int(m.sum()) == int(st[1]) == 4080
         assert abs(mae - st[0]) < 2e-3 and abs(kl - st[2]) < 2e-3 * max(1.0, abs(st[2]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# eval path next to the encoder: reference Fusion gate + lin_test, STGCN's GLU temporal convolution
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eval_path():
+    return np.load(os.path.join(GOLDEN, "eval_path.npz"))
+
+
+def test_eval_glue_oracle_matches_reference_fusion(eval_path):
+    g = eval_path
+    D, ibd = (int(v) for v in g["glue.dims"])
+    P = {k[len("glue.p."):]: T(g[k]).requires_grad_() for k in g.files if k.startswith("glue.p.")}
+    x_pre = T(g["glue.x_pre"]).requires_grad_()
+    y = O.eval_glue(T(g["glue.source"]), x_pre, P, ibd)
+    close(y, T(g["glue.out"]), what="eval glue out")
+    y.backward(T(g["glue.gout"]))
+    close(x_pre.grad, T(g["glue.g.x_pre"]), atol=1e-4, rtol=1e-4, what="eval glue d x_pre")
+    assert len(P) == 8
+    for k, v in P.items():
+        close(v.grad, T(g["glue.g." + k]), atol=1e-4, rtol=1e-4, what="eval glue grad " + k)
+
+
+@pytest.mark.parametrize("tag", ["same", "narrow", "widen", "wide_kernel"])
+def test_temporal_conv_glu_oracle_matches_reference_stgcn(eval_path, tag):
+    g, pre = eval_path, f"glu.{tag}."
+    x = T(g[pre + "x"]).requires_grad_()
+    w, b = T(g[pre + "conv.weight"]).requires_grad_(), T(g[pre + "conv.bias"]).requires_grad_()
+    aw = T(g[pre + "align.weight"]).requires_grad_() if pre + "align.weight" in g.files else None
+    ab = T(g[pre + "align.bias"]).requires_grad_() if aw is not None else None
+    y = O.temporal_conv_glu(x, w, b, aw, ab)
+    close(y, T(g[pre + "out"]), what="GLU out " + tag)
+    y.backward(T(g[pre + "gout"]))
+    close(x.grad, T(g[pre + "g.x"]), atol=1e-4, rtol=1e-4, what="GLU dx " + tag)
+    close(w.grad, T(g[pre + "g.conv.weight"]), atol=1e-4, rtol=1e-4, what="GLU dW " + tag)
+    close(b.grad, T(g[pre + "g.conv.bias"]), atol=1e-4, rtol=1e-4, what="GLU db " + tag)
+    if aw is not None:
+        close(aw.grad, T(g[pre + "g.align.weight"]), atol=1e-4, rtol=1e-4, what="GLU d align W " + tag)
+        close(ab.grad, T(g[pre + "g.align.bias"]), atol=1e-4, rtol=1e-4, what="GLU d align b " + tag)
