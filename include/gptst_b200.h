@@ -178,6 +178,16 @@ int gptst_sum_partials(const float* const* ins, float* const* outs, const long* 
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
+/* EXPERIMENTAL third generation of gptst_gproj_fwd / _bwd for D = 64 (csrc/gproj3.cu; not used by the Python side yet): the forward
+ * also writes a packed sign mask of Y (mask: (rows, 2) uint32, 64 bits per row of Y in Y's memory order, bit c = Y[row][c] > 0;
+ * may be NULL) and the backward reads that mask instead of Y (LeakyReLU's derivative needs nothing else: 4A instead of 5A of
+ * traffic) and scales its fp16 operands per warp tile instead of per CTA chunk (no block-wide max exchanges).  flags as in
+ * gptst_linear_bwd_acc: bit 0 = dX accumulated in place, bit 1 = W / dW are [out][in].  splits = gptst_gproj_splits(G, R, D).   */
+int gptst_gproj3_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, void* mask, int G, int R,
+                     long group_stride, long row_stride, int D, int act, int prec, void* stream);
+int gptst_gproj3_bwd(const float* dY, const void* mask, const float* X, const float* W, float* dX, float* dW_part,
+                     float* dbias_part, float* dRes, int G, int R, long group_stride, long row_stride, int D, int act, int prec,
+                     int splits, int flags, void* stream);
 /* decoder output projection dim_flow_out = nn.Linear(D, O), O = input_base_dim <= 4 (GPTST.py:454-458), replacing
  * `self.dim_flow_out(flow_decode)` and its autograd: y (rows,O) = x (rows,D) W^T + b, W (O,D) as nn.Linear stores it, D = 64|128.
  * Backward in one pass: dX (rows,D) = dy W (may be NULL) and part (parts, O*D + O) = per-CTA partials of dW = dy^T x
