@@ -7,6 +7,8 @@
 //   * ONE power-of-two scale per WARP tile instead of per CTA chunk: dX is a per-warp product anyway, and for dW the
 //     un-scaling moves into the row-tile loop (dW += dW_tile * (sx_tile * sg_tile)), which removes both block-wide max
 //     exchanges and their barriers (17 % of the stall samples).
+//   * (added after the check of profiles/gproj3_check_r01.log, not yet timed) with dX accumulated in place the old dX rows
+//     are prefetched into L2 together with the staging copies: their read in the epilogue was 27 % of the stall samples.
 // Everything else (staging, operand layouts, dW ownership, determinism) is unchanged, see gproj2.cu.
 #include <cstdlib>
 
@@ -33,6 +35,14 @@ __device__ __forceinline__ void stage16(unsigned char* slots, const float* base,
         if (r0 + r < R) cp_async16(dst, base + (long)(r0 + r) * rs + ch * 4);
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// the two 128-byte lines of each of the warp's 16 rows (the read-modify-write of dX in the epilogue then finds them in L2)
+__device__ __forceinline__ void prefetch_rows16(const float* base, long rs, int r0, int R, int lane) {
+    const int r = lane >> 1, half = lane & 1;
+    if (r0 + r < R) prefetch_l2(base + (long)(r0 + r) * rs + 32 * half);
 }
 
 __device__ __forceinline__ int kperm(int j) {   // physical k (mod 16) -> logical MMA k of the ldmatrix-from-fp32 A operand
@@ -179,6 +189,7 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
         cp_async_commit();
         stage16(Xs + (size_t)n0 * ROWB, Xg, rs, r0, R, lane);
         cp_async_commit();
+        if (flags & 1) prefetch_rows16(dXg, rs, r0, R, lane);
     }
     const float* Wg = W + (size_t)grp * D * D;
     {   // issue all W_g loads of this thread first, convert afterwards
@@ -228,6 +239,7 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
             cp_async_commit();
             stage16(Xw, Xg, rs, r0, R, lane);
             cp_async_commit();
+            if (flags & 1) prefetch_rows16(dXg, rs, r0, R, lane);
         }
         // sign mask of the warp's 16 rows: lane r < 16 holds row r0 + r (one 8-byte load, issued before the dY wait)
         uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu;
