@@ -6,6 +6,9 @@ O=gpurun_out
 mkdir -p $O
 T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
+# stand-alone C++ checks first: no Python start-up, a few seconds each (build them here: see the header of each .cu)
+[ -x tools/kbench ] && timeout 20 ./tools/kbench > $O/kbench.log 2>&1 && el "kbench: $(grep -c ' us ' $O/kbench.log) kernels timed"
+[ -x tools/gproj3_check ] && timeout 20 ./tools/gproj3_check > $O/gproj3_check.log 2>&1 && el "gproj3_check done"
 timeout 80 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -v "Warning\|warnings.warn\|run_backward\|^$" | tail -30 > $O/pt_b.log
 el "pytest: $(tail -1 $O/pt_b.log)"
 timeout 70 python bench.py > $O/bench_v.json 2> $O/bench_v.err
