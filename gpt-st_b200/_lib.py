@@ -65,6 +65,7 @@ SIGNATURES = {
     "gptst_affine1_bwd": (_i, [_f, _f, _f, _l, _i, _i, _f]),
     "gptst_gproj3_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _f]),
     "gptst_gproj3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _i, _i, _f]),
+    "gptst_tmix3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_proj_out_fwd": (_i, [_f, _f, _f, _f, _l, _i, _i, _f]),
     "gptst_proj_out_bwd_parts": (_i, [_l]),
     "gptst_proj_out_bwd": (_i, [_f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),

@@ -162,6 +162,21 @@ def gproj3_bwd(dY, mask, X, W, *, act: bool, prec: int, want_dres: bool):
     return dX, dW, db, dres
 
 
+def tmix3_bwd(dy, x, M, dout, mask, prec):
+    """EXPERIMENTAL (csrc/tmix3.cu): (dx, dM partials) with dx = dout * act'(mask) + M^T o dy written in one pass -- the companion of
+    `gproj3_bwd(..., want_dres=False)`; kernel-level check in tools/gproj3_check.cu."""
+    B, T, N, D = x.shape
+    dy, x, M, dout = _c(dy), _c(x), _c(M), _c(dout)
+    _chk(dy, x, M, dout)
+    L = _lib.lib()
+    splits = L.gptst_tmix_bwd_splits(B, N)
+    dx = torch.empty_like(x)
+    part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
+    rc = L.gptst_tmix3_bwd(_p(dy), _p(x), _p(M), _p(dout), _p(mask), _p(dx), _p(part), B, T, N, D, prec, splits, _stream())
+    _lib.check(rc, "gptst_tmix3_bwd")
+    return dx, part
+
+
 def tmix(x, M, out=None, *, transpose=False, accumulate=False):
     B, T, N, D = x.shape
     x, M = _c(x), _c(M)
@@ -286,6 +301,12 @@ class _HyperTemCore(torch.autograd.Function):
     def backward(ctx, dout):
         eb, Mn, W, ret, out = ctx.saved_tensors           # `out` is the sign mask on the experimental path
         dout = dout.contiguous()
+        if ctx.use3 and os.environ.get("GPTST_B200_TMIX3", "0") == "1":
+            # experimental pair: no dRes store in the projection backward, the mix backward rebuilds it from dout and the mask
+            B, T, N, D = eb.shape
+            dret, dW, db, _ = gproj3_bwd(dout, out, ret, W, act=True, prec=ctx.prec, want_dres=False)
+            deb, dM_part = tmix3_bwd(dret, eb, Mn, dout, out, ctx.prec)
+            return deb, dM_part, dW.view(B, T, D, D), db.view(B, T, D), None
         if ctx.use3:
             dret, dW, db, deb = gproj3_bwd(dout, out, ret, W, act=True, prec=ctx.prec, want_dres=True)
         else:

@@ -188,6 +188,11 @@ int gptst_gproj3_fwd(const float* X, const float* W, const float* bias, const fl
 int gptst_gproj3_bwd(const float* dY, const void* mask, const float* X, const float* W, float* dX, float* dW_part,
                      float* dbias_part, float* dRes, int G, int R, long group_stride, long row_stride, int D, int act, int prec,
                      int splits, int flags, void* stream);
+/* EXPERIMENTAL companion of gptst_gproj3_bwd for hyperTem (csrc/tmix3.cu; not used by the Python side yet): gptst_tmix_bwd with the
+ * residual gradient rebuilt in the kernel, dx_out = dout * act'(mask) + M^T o dy (written, not accumulated), so that the projection
+ * backward can skip its dRes store (dRes = NULL).  mask as written by gptst_gproj3_fwd, or NULL for act' = 1.                       */
+int gptst_tmix3_bwd(const float* dy, const float* x, const float* M, const float* dout, const void* mask, float* dx_out,
+                    float* dM_part, int B, int T, int N, int D, int prec, int splits, void* stream);
 /* decoder output projection dim_flow_out = nn.Linear(D, O), O = input_base_dim <= 4 (GPTST.py:454-458), replacing
  * `self.dim_flow_out(flow_decode)` and its autograd: y (rows,O) = x (rows,D) W^T + b, W (O,D) as nn.Linear stores it, D = 64|128.
  * Backward in one pass: dX (rows,D) = dy W (may be NULL) and part (parts, O*D + O) = per-CTA partials of dW = dy^T x

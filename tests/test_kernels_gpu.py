@@ -536,8 +536,9 @@ def test_deferred_partial_sums_through_tables():
 
 @pytest.mark.skipif(__import__("os").environ.get("GPTST_B200_EXPERIMENTAL", "0") != "1",
                     reason="experimental kernels (csrc/gproj3.cu) are opt-in: set GPTST_B200_EXPERIMENTAL=1")
+@pytest.mark.parametrize("tmix3", ["0", "1"])
 @pytest.mark.parametrize("B,N", [(2, 23), (2, 170), (3, 207)])
-def test_hypertem_block_with_sign_mask_projection(B, N, monkeypatch):
+def test_hypertem_block_with_sign_mask_projection(B, N, tmix3, monkeypatch):
     """GPTST_B200_GPROJ3=1: hyperTem through the sign-mask projection kernels gives the default path's outputs and gradients
     (kernel-level agreement on the B200: profiles/gproj3_check_r01.log)."""
     from gptst_b200 import ops
@@ -548,6 +549,7 @@ def test_hypertem_block_with_sign_mask_projection(B, N, monkeypatch):
 
     def run(flag):
         monkeypatch.setenv("GPTST_B200_GPROJ3", flag)
+        monkeypatch.setenv("GPTST_B200_TMIX3", tmix3 if flag == "1" else "0")
         ins = [t.clone().requires_grad_() for t in (eb, Mn, W, b)]
         out = ops.hypertem_core(*ins, 3)
         out.backward(go)

@@ -21,6 +21,10 @@ typedef int (*bwd2_t)(const float*, const float*, const float*, const float*, fl
 typedef int (*fwd3_t)(const float*, const float*, const float*, const float*, float*, void*, int, int, long, long, int, int, int, void*);
 typedef int (*bwd3_t)(const float*, const void*, const float*, const float*, float*, float*, float*, float*, int, int, long, long, int, int,
                       int, int, int, void*);
+typedef int (*tmixb_t)(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, void*);
+typedef int (*tmix3b_t)(const float*, const float*, const float*, const float*, const void*, float*, float*, int, int, int, int, int, int,
+                        void*);
+typedef int (*tsplits_t)(int, int);
 typedef int (*splits_t)(int, int, int);
 typedef int (*lsplits_t)(long, int);
 typedef int (*lacc_t)(const float*, const float*, const float*, float*, float*, float*, long, int, int, int, void*);
@@ -91,7 +95,10 @@ int main() {
     splits_t splits_f = (splits_t)dlsym(L, "gptst_gproj_splits");
     lsplits_t lsplits_f = (lsplits_t)dlsym(L, "gptst_linear_bwd_acc_splits");
     lacc_t lacc = (lacc_t)dlsym(L, "gptst_linear_bwd_acc");
-    if (!fwd2 || !bwd2 || !fwd3 || !bwd3 || !splits_f || !lsplits_f || !lacc) { printf("missing symbol\n"); return 1; }
+    tmixb_t tmixb = (tmixb_t)dlsym(L, "gptst_tmix_bwd");
+    tmix3b_t tmix3b = (tmix3b_t)dlsym(L, "gptst_tmix3_bwd");
+    tsplits_t tsplits_f = (tsplits_t)dlsym(L, "gptst_tmix_bwd_splits");
+    if (!fwd2 || !bwd2 || !fwd3 || !bwd3 || !splits_f || !lsplits_f || !lacc || !tmixb || !tmix3b || !tsplits_f) { printf("missing symbol\n"); return 1; }
 
     const int B = 64, T = 12, N = 170, D = 64;
     const size_t M = (size_t)B * T * N, A = M * D;
@@ -108,6 +115,13 @@ int main() {
     fill<<<592, 256>>>(X, A, 1u, 1.f); fill<<<592, 256>>>(Res, A, 2u, 1.f); fill<<<592, 256>>>(dY, A, 3u, 0.01f);
     fill<<<592, 256>>>(Wt, (size_t)B * T * D * D, 4u, 0.125f); fill<<<592, 256>>>(Wn, (size_t)N * D * D, 5u, 0.125f);
     fill<<<592, 256>>>(bt, (size_t)B * T * D, 6u, 0.5f); fill<<<592, 256>>>(bn, (size_t)N * D, 7u, 0.5f);
+    CK(cudaDeviceSynchronize());
+
+    // hyperTem backward pair: mix matrix and dM partial buffers
+    const int spm = tsplits_f(B, N);
+    float *Mn, *dM2, *dM3;
+    CK(cudaMalloc(&Mn, (size_t)N * T * T * 4)); CK(cudaMalloc(&dM2, (size_t)spm * N * T * T * 4)); CK(cudaMalloc(&dM3, (size_t)spm * N * T * T * 4));
+    fill<<<592, 256>>>(Mn, (size_t)N * T * T, 8u, 0.2f);
     CK(cudaDeviceSynchronize());
 
     struct Case { const char* name; int G, R; long gs, rs; const float *W, *b; };
@@ -139,6 +153,21 @@ int main() {
         const float tb3 = time_it([&] { bwd3(dY, mask, X, c.W, dX3, dW3, db3, dR3, c.G, c.R, c.gs, c.rs, D, 1, 3, sp, 0, 0); }, 20);
         CK(cudaDeviceSynchronize());
         printf("  time per launch (us): fwd v2 %.1f  v3(+mask) %.1f | bwd v2 %.1f  v3 %.1f\n", tf2, tf3, tb2, tb3);
+        if (c.G == B * T) {
+            // the whole hyperTem backward: default pair (projection backward writes dRes, the mix backward accumulates into it) against
+            // the experimental pair (no dRes store; the mix backward rebuilds dOut * act' from dOut and the sign mask).  eb := Res.
+            auto pair2 = [&] { return bwd2(dY, Y2, X, c.W, dX2, dW2, db2, dR2, c.G, c.R, c.gs, c.rs, D, 1, 3, sp, 0) |
+                                      tmixb(dX2, Res, Mn, dR2, dM2, B, T, N, D, 3, spm, 0); };
+            auto pair3 = [&] { return bwd3(dY, mask, X, c.W, dX3, dW3, db3, 0, c.G, c.R, c.gs, c.rs, D, 1, 3, sp, 0, 0) |
+                                      tmix3b(dX3, Res, Mn, dY, mask, dR3, dM3, B, T, N, D, 3, spm, 0); };
+            rc = pair2(); rc3 = pair3();
+            CK(cudaDeviceSynchronize());
+            printf("  hyperTem backward pair rc v2=%d v3=%d (tmix splits %d)\n", rc, rc3, spm);
+            report("d eb", dR3, dR2, A); report("dM_part", dM3, dM2, (size_t)spm * N * T * T);
+            const float tp2 = time_it([&] { pair2(); }, 20), tp3 = time_it([&] { pair3(); }, 20);
+            CK(cudaDeviceSynchronize());
+            printf("  time per pair (us): default (gproj_bwd + tmix_bwd) %.1f  experimental (gproj3_bwd without dRes + tmix3_bwd) %.1f\n", tp2, tp3);
+        }
     }
     {   // shared weight, dX accumulated in place (ln_p of cap): gptst_linear_bwd_acc vs gproj3 with flags = 3
         const int sp = lsplits_f((long)M, D);
