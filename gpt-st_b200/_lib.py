@@ -28,6 +28,7 @@ SIGNATURES = {
     "gptst_cap_recon": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_e1": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon_hop": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_recon_hop3": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon_hop_fused": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_dv_dcr": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),

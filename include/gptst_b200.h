@@ -77,6 +77,10 @@ int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const 
  * the backward pass.  Opt-in (GPTST_B200_HOP=fused): measured slower than the split pair on the B200 (80 us vs 6.5 + 22 us).   */
 int gptst_cap_recon_hop_fused(const float* c, const float* s, const float* dyn, float* e1, float* v, float* recon, int B, int T,
                               int N, int D, int H, int HT, void* stream);
+/* EXPERIMENTAL variant of gptst_cap_recon_hop (csrc/cap_hop3.cu; not used by the Python side yet): the thread's column quad of every
+ * v row is kept in registers across the nodes it reconstructs (5x fewer shared-memory reads); bit-identical results expected.    */
+int gptst_cap_recon_hop3(const float* c, const float* s, const float* dyn, const float* e1, float* v, float* recon, int B, int T,
+                         int N, int D, int H, int HT, void* stream);
 /* ---- cap backward pieces ------------------------------------------------------
  * dv = c drecon, dcr = v drecon^T                                                                            */
 int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int B, int T, int N,

@@ -183,6 +183,31 @@ int main() {
         CK(cudaDeviceSynchronize());
         printf("  time per launch (us): v2 %.1f  v3 %.1f\n", t2, t3);
     }
+    {   // cap_recon_hop3 (v rows held in registers) against cap_recon_hop on real routing outputs
+        typedef int (*route_t)(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, int, void*);
+        typedef int (*e1_t)(const float*, const float*, float*, int, int, int, int, int, void*);
+        typedef int (*rh_t)(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, void*);
+        route_t route = (route_t)dlsym(L, "gptst_cap_route_fwd");
+        e1_t hop_e1 = (e1_t)dlsym(L, "gptst_cap_hop_e1");
+        rh_t rh2 = (rh_t)dlsym(L, "gptst_cap_recon_hop"), rh3 = (rh_t)dlsym(L, "gptst_cap_recon_hop3");
+        if (!route || !hop_e1 || !rh2 || !rh3) { printf("missing symbol (recon_hop)\n"); return 1; }
+        const int H = 10, HT = 16;
+        const size_t C = M * H, S = (size_t)B * T * H * D;
+        float *dadj, *dyn, *cc, *ss, *e1, *v2, *v3;
+        CK(cudaMalloc(&dadj, C * 4)); CK(cudaMalloc(&cc, C * 4)); CK(cudaMalloc(&ss, S * 4)); CK(cudaMalloc(&v2, S * 4)); CK(cudaMalloc(&v3, S * 4));
+        CK(cudaMalloc(&dyn, (size_t)B * HT * T * H * 4)); CK(cudaMalloc(&e1, (size_t)B * HT * D * 4));
+        fill<<<592, 256>>>(dadj, C, 9u, 1.f); fill<<<592, 256>>>(dyn, (size_t)B * HT * T * H, 10u, 0.3f);
+        int rc = route(X, Wn, bn, dadj, cc, ss, B, T, N, D, H, 2, 3, 0);          // Wn / bn: any (64,64) weight and (64) bias
+        rc |= hop_e1(ss, dyn, e1, B, T, D, H, HT, 0);
+        const int r2 = rh2(cc, ss, dyn, e1, v2, Y2, B, T, N, D, H, HT, 0), r3 = rh3(cc, ss, dyn, e1, v3, Y3, B, T, N, D, H, HT, 0);
+        CK(cudaDeviceSynchronize());
+        printf("== cap recon_hop: route/hop_e1 rc=%d, recon_hop rc v2=%d v3=%d\n", rc, r2, r3);
+        report("recon", Y3, Y2, A); report("v", v3, v2, S);
+        const float t2 = time_it([&] { rh2(cc, ss, dyn, e1, v2, Y2, B, T, N, D, H, HT, 0); }, 20);
+        const float t3 = time_it([&] { rh3(cc, ss, dyn, e1, v3, Y3, B, T, N, D, H, HT, 0); }, 20);
+        CK(cudaDeviceSynchronize());
+        printf("  time per launch (us): v2 %.1f  v3 %.1f\n", t2, t3);
+    }
     cudaError_t e = cudaGetLastError();
     printf("last CUDA error: %s\n", cudaGetErrorString(e));
     return e == cudaSuccess ? 0 : 2;

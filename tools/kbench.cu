@@ -27,6 +27,7 @@ typedef int (*tmix_bwd_t)(cf, cf, cf, float*, float*, int, int, int, int, int, i
 typedef int (*cap_route_fwd_t)(cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, int, void*);
 typedef int (*cap_hop_e1_t)(cf, cf, float*, int, int, int, int, int, void*);
 typedef int (*cap_recon_hop_t)(cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, void*);
+typedef cap_recon_hop_t cap_recon_hop3_t;
 typedef int (*cap_dv_dcr_hoprows_t)(cf, cf, cf, cf, cf, cf, float*, float*, float*, int, int, int, int, int, int, void*);
 typedef int (*cap_hop_bwd_parts_t)(int);
 typedef int (*cap_hop_bwd_cols_t)(cf, cf, cf, cf, cf, float*, float*, int, int, int, int, int, void*);
@@ -82,7 +83,7 @@ int main(int argc, char** argv) {
     void* L = dlopen("gpt-st_b200/libgptst_b200.so", RTLD_NOW);
     if (!L) { printf("dlopen failed: %s\n", dlerror()); return 1; }
     SYM(gproj_fwd) SYM(gproj_splits) SYM(gproj_bwd) SYM(gproj3_fwd) SYM(gproj3_bwd) SYM(tmix) SYM(tmix_bwd_splits) SYM(tmix_bwd)
-    SYM(cap_route_fwd) SYM(cap_hop_e1) SYM(cap_recon_hop) SYM(cap_dv_dcr_hoprows) SYM(cap_hop_bwd_parts) SYM(cap_hop_bwd_cols)
+    SYM(cap_route_fwd) SYM(cap_hop_e1) SYM(cap_recon_hop) SYM(cap_recon_hop3) SYM(cap_dv_dcr_hoprows) SYM(cap_hop_bwd_parts) SYM(cap_hop_bwd_cols)
     SYM(cap_route_bwd_dz) SYM(linear_bwd_acc_splits) SYM(linear_bwd_acc) SYM(proj_out_fwd) SYM(proj_out_bwd_parts) SYM(proj_out_bwd)
     SYM(score_head_fwd)
 
@@ -132,6 +133,7 @@ int main(int argc, char** argv) {
     bench("cap_route_fwd (routing)    fwd", Ab + 2 * Cb, iters, [&](int i) { return cap_route_fwd(st[i].x, Wp, bp, dadj, st[i].c, st[i].s, B, T, N, D, H, RT, prec, 0); });
     bench("cap_hop_e1                 fwd", 0.1 * Ab, iters, [&](int i) { return cap_hop_e1(st[i].s, dyn, st[i].e1, B, T, D, H, HT, 0); });
     bench("cap_recon_hop              fwd", Ab + Cb, iters, [&](int i) { return cap_recon_hop(st[i].c, st[i].s, dyn, st[i].e1, st[i].v, st[i].recon, B, T, N, D, H, HT, 0); });
+    bench("cap_recon_hop3             fwd (experimental)", Ab + Cb, iters, [&](int i) { return cap_recon_hop3(st[i].c, st[i].s, dyn, st[i].e1, st[i].v, st[i].recon, B, T, N, D, H, HT, 0); });
     bench("gproj node-grouped         fwd", 3 * Ab, iters, [&](int i) { return gproj_fwd(st[i].recon, Wn, bn, st[i].x, st[i].out_n, N, B * T, gsN, rsN, D, 1, prec, 0); });
     bench("gproj node-grouped         bwd", 5 * Ab, iters, [&](int i) { return gproj_bwd(st[i].dout, st[i].out_n, st[i].recon, Wn, st[i].drecon, dWnp, dbnp, st[i].dx, N, B * T, gsN, rsN, D, 1, prec, sp_n, 0); });
     bench("cap_dv_dcr_hoprows         bwd", Ab + 2 * Cb, iters, [&](int i) { return cap_dv_dcr_hoprows(st[i].c, st[i].v, st[i].drecon, st[i].s, dyn, st[i].e1, st[i].dcr, st[i].dr, st[i].dp2, B, T, N, D, H, HT, 0); });
