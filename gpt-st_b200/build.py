@@ -1,6 +1,6 @@
 """Build libgptst_b200.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
 
-    python gpt-st_b200/build.py [--force]
+    python gpt-st_b200/build.py [--force] [--tools]
 
 No torch / pybind dependency: the library is a plain C-ABI shared object loaded with ctypes.
 Objects are compiled in parallel and cached by source mtime under csrc/_build/.
@@ -61,5 +61,21 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+def build_tools(verbose: bool = True) -> None:
+    """Stand-alone C++ checks under tools/ (kbench, gproj3_check): they dlopen the library, so they only need nvcc + libdl."""
+    tools = os.path.join(os.path.dirname(HERE), "tools")
+    for name in ("kbench", "gproj3_check"):
+        src, exe = os.path.join(tools, name + ".cu"), os.path.join(tools, name)
+        if os.path.isfile(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
+            continue
+        r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-o", exe, src, "-ldl"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for tools/{name}.cu:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[gptst_b200] built tools/{name}")
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    if "--tools" in sys.argv:
+        build_tools()
