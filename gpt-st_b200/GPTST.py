@@ -137,13 +137,20 @@ class hyperTem(nn.Module):
         Mn = ops.mix_matrix(A) if A.is_cuda else torch.einsum("nht,nhs->nts", A, A)   # two hops, no nonlinearity in between
         W = ops.lowrank_table(time_eb, self.weights_pool)               # einsum("btd,dio->btio")
         bias = ops.lowrank_table(time_eb, self.bias_pool)
+        if Mn.is_cuda and ops.hypertem_fused_enabled(W.shape[-1], Mn.shape[-1], ops.default_precision()):
+            # fused block: the parameter-side node lives on THIS stream, so dM_n / dW_bt / db_bt are computed here in backward
+            Mn, W, bias, mb = ops.hypertem_params(Mn, W, bias)
+            return Mn, W, bias, mb["wf"], mb["wb"], mb
         if Mn.is_cuda:
             # (P, N, T, T) stride-0 view: the dM_n partials of the backward are summed on this stream (ops.expand_partials)
             Mn = ops.expand_partials(Mn, ops.hypertem_partial_count(time_eb.shape[0], Mn.shape[0], W.shape[-1]))
         return Mn, W, bias
 
     def forward(self, eb, node_embeddings, time_eb, tables=None):
-        Mn, W, bias = tables if tables is not None else self.tables(node_embeddings, time_eb)
+        tb = tables if tables is not None else self.tables(node_embeddings, time_eb)
+        if len(tb) == 6:
+            return ops.hypertem_fused(eb, tb[0], tb[1], tb[2], tb[5])
+        Mn, W, bias = tb
         return ops.hypertem_core(eb, Mn, W, bias)
 
 

@@ -67,6 +67,13 @@ SIGNATURES = {
     "gptst_gproj3_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _f]),
     "gptst_gproj3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _i, _i, _f]),
     "gptst_tmix3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_hypertem_wfrag_bytes": (_l, [_i]),
+    "gptst_hypertem_mask_pad_rows": (_i, []),
+    "gptst_hypertem_pack_w": (_i, [_f, _f, _f, _i, _f]),
+    "gptst_hypertem_fwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
+    "gptst_hypertem_bwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
+    "gptst_hypertem_dw": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_tmix_dM2": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_proj_out_fwd": (_i, [_f, _f, _f, _f, _l, _i, _i, _f]),
     "gptst_proj_out_bwd_parts": (_i, [_l]),
     "gptst_proj_out_bwd": (_i, [_f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),

@@ -161,8 +161,10 @@ template <int NW, int MINB, int PREC>
 __global__ void __launch_bounds__(NW * 32, MINB)
 gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, const float* __restrict__ X,
                   const float* __restrict__ W, float* __restrict__ dX, float* __restrict__ dWp, float* __restrict__ dbp,
-                  float* __restrict__ dRes, int G, int R, long gs, long rs, int act, int cps, int flags) {
-    // flags: bit 0 = dX is accumulated in place (dX += dy W^T); bit 1 = W and dW are [out][in] (a shared nn.Linear weight)
+                  float* __restrict__ dRes, int G, int R, long gs, long rs, int act, int cps, int flags, int mrs) {
+    // flags: bit 0 = dX is accumulated in place (dX += dy W^T); bit 1 = W and dW are [out][in] (a shared nn.Linear weight);
+    //        bit 2 = dW / db only (no W, no dX: the side-stream half of the fused hyperTem backward, csrc/htem_fused.cu);
+    //        bit 3 = the mask comes from the fused hyperTem forward: `mrs` words per group, bit 16*(c & 3) + (c >> 2) = column c
     constexpr int TPW = (32 + NW - 1) / NW;          // (16 x 8) dW output tiles per warp
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned char* Xs = smraw;                                      // [NW*16][ROWB]
@@ -192,7 +194,7 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
         if (flags & 1) prefetch_rows16(dXg, rs, r0, R, lane);
     }
     const float* Wg = W + (size_t)grp * D * D;
-    {   // issue all W_g loads of this thread first, convert afterwards
+    if (!(flags & 4)) {   // issue all W_g loads of this thread first, convert afterwards
         constexpr int WI = (D * 16 + NT - 1) / NT;
         float4 wv[WI];
 #pragma unroll
@@ -244,7 +246,7 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
         // sign mask of the warp's 16 rows: lane r < 16 holds row r0 + r (one 8-byte load, issued before the dY wait)
         uint32_t mlo = 0xffffffffu, mhi = 0xffffffffu;
         if (act && lane < 16 && r0 + lane < R) {
-            const uint2 m = Mask[((long)grp * gs + (long)(r0 + lane) * rs) / D];
+            const uint2 m = (flags & 8) ? Mask[(long)grp * mrs + r0 + lane] : Mask[((long)grp * gs + (long)(r0 + lane) * rs) / D];
             mlo = m.x; mhi = m.y;
         }
         cp_async_wait_group<1>();
@@ -272,7 +274,11 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
                 f[k] = *reinterpret_cast<const float4*>(Gw + (size_t)r * ROWB + ch * 16);
                 // the row's mask words come from lane r (every lane takes part in the shuffles); bits 4ch .. 4ch+3 are this chunk's
                 const uint32_t lo_r = __shfl_sync(0xffffffffu, mlo, r), hi_r = __shfl_sync(0xffffffffu, mhi, r);
-                const uint32_t bits = ((ch < 8 ? lo_r : hi_r) >> ((4 * ch) & 31)) & 15u;
+                uint32_t bits = ((ch < 8 ? lo_r : hi_r) >> ((4 * ch) & 31)) & 15u;
+                if (flags & 8) {
+                    const uint32_t mx = lo_r >> ch, my = hi_r >> ch;
+                    bits = (mx & 1u) | ((mx >> 15) & 2u) | ((my & 1u) << 2) | ((my >> 13) & 8u);
+                }
                 if (r0 + r < R) {
                     if (act) {
                         f[k].x = (bits & 1u) ? f[k].x : kSlope * f[k].x; f[k].y = (bits & 2u) ? f[k].y : kSlope * f[k].y;
@@ -296,7 +302,7 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
             __syncwarp();
         }
         // ---- dX = dy W_g^T for the warp's 16 rows (two halves of 4 column tiles to keep the accumulators small)
-        {
+        if (!(flags & 4)) {
             const float un = sg.y * (1.f / WSCALE);
 #pragma unroll
             for (int hf2 = 0; hf2 < 2; ++hf2) {
@@ -460,14 +466,14 @@ static cudaError_t launch_fwd(const float* X, const float* W, const float* bias,
 
 template <int NW, int MINB, int PREC>
 static cudaError_t launch_bwd(const float* dY, const uint2* Mask, const float* X, const float* W, float* dX, float* dWp,
-                              float* dbp, float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, cudaStream_t st) {
+                              float* dbp, float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, int mrs, cudaStream_t st) {
     const int chunks = (R + NW * 16 - 1) / (NW * 16);
     const int cps = (chunks + splits - 1) / splits;
     const size_t smem = (size_t)2 * NW * 16 * ROWB + (size_t)D * ROWB + (size_t)(2 * NW) * 4;
     auto kern = gproj3_bwd_kernel<NW, MINB, PREC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<dim3(G, splits), NW * 32, smem, st>>>(dY, Mask, X, W, dX, dWp, dbp, dRes, G, R, gs, rs, act, cps, flags);
+    kern<<<dim3(G, splits), NW * 32, smem, st>>>(dY, Mask, X, W, dX, dWp, dbp, dRes, G, R, gs, rs, act, cps, flags, mrs);
     return cudaGetLastError();
 }
 
@@ -488,8 +494,8 @@ static cudaError_t fwd_p(const float* X, const float* W, const float* bias, cons
 }
 template <int PREC>
 static cudaError_t bwd_p(const float* dY, const uint2* Mask, const float* X, const float* W, float* dX, float* dWp, float* dbp,
-                         float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, cudaStream_t st) {
-    GP2_DISPATCH(launch_bwd, dY, Mask, X, W, dX, dWp, dbp, dRes, G, R, gs, rs, act, splits, flags, st)
+                         float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, int mrs, cudaStream_t st) {
+    GP2_DISPATCH(launch_bwd, dY, Mask, X, W, dX, dWp, dbp, dRes, G, R, gs, rs, act, splits, flags, mrs, st)
 }
 
 }  // namespace gp3
@@ -522,7 +528,18 @@ extern "C" int gptst_gproj3_bwd(const float* dY, const void* mask, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == PREC_3XTF32)
         return (int)gp3::bwd_p<PREC_3XTF32>(dY, (const uint2*)mask, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride,
-                                            act, splits, flags, st);
+                                            act, splits, flags, 0, st);
     return (int)gp3::bwd_p<PREC_TF32>(dY, (const uint2*)mask, X, W, dX, dW_part, dbias_part, dRes, G, R, group_stride, row_stride, act,
-                                      splits, flags, st);
+                                      splits, flags, 0, st);
+}
+
+// Side-stream half of the fused hyperTem backward (csrc/htem_fused.cu): dW_bt = ret_bt^T dy_bt and db_bt = sum_n dy_bt for every
+// (b, t), dy = dOut . LeakyReLU'(mask).  mask: the fused forward's sign words, `mask_rows` per (b, t).  Partials: (splits, B*T, ..)
+// with splits = gptst_gproj_splits(B*T, N, 64).   Reference: GPTST.py:160-162, SURVEY.md appendix A (G_bt, sigma_bt).
+extern "C" int gptst_hypertem_dw(const float* dout, const void* mask, const float* ret, float* dW_part, float* dbias_part, int B, int T,
+                                 int N, int D, int mask_rows, int splits, void* stream) {
+    if (!dout || !mask || !ret || !dW_part || !dbias_part || B <= 0 || T <= 0 || N <= 0 || splits <= 0) return -1;
+    if (D != 64 || mask_rows < N) return -2;
+    return (int)gp3::bwd_p<PREC_3XTF32>(dout, (const uint2*)mask, ret, ret, dW_part, dW_part, dbias_part, nullptr, B * T, N, (long)N * D,
+                                        (long)D, 1, splits, 4 | 8, mask_rows, (cudaStream_t)stream);
 }

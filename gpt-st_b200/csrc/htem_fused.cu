@@ -20,7 +20,7 @@
 //   * work is pipelined in three rounds of four time steps: [mix/epilogue phase] -> barrier -> [MMA phase] -> barrier; two CTAs
 //     per SM run out of phase, so the FMA pipe of one overlaps the tensor pipe of the other.
 //   * the epilogue runs in the mix layout (coalesced 16-byte stores of full rows); the LeakyReLU sign mask (8 bytes per row,
-//     bit c = out[c] > 0) is assembled with redux.sync.
+//     bit 16*(c & 3) + (c >> 2) = out[c] > 0: the order four warp ballots deliver) costs four votes and two byte permutes.
 // What is NOT here: the parameter-side gradients (dW_bt = ret^T dy, dM_n = dret . eb) -- nothing on the main chain reads
 // them, so they are computed by side-stream kernels from `ret` / `dret` (gproj3 dW-only mode, tmix dM-only mode).
 #include <cuda.h>
@@ -102,18 +102,23 @@ __global__ void __launch_bounds__(256) htem_pack_kernel(const float* __restrict_
 }
 
 // ---- pieces shared by both directions ----------------------------------------------------------------------------
-// max |.| over the 16 lanes that share a node (a row of 64 columns)
-__device__ __forceinline__ float row_absmax(const float4& v) {
-    float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    return m;
+// max |.| over the warp = the two rows (nodes) it holds; non-negative floats order like their bit patterns, so ONE redux.sync
+// replaces a four-step shuffle chain.  A scale shared by two rows is as good as a per-row one: the split keeps 22 bits for
+// every element within 2^16 of the scaled maximum and an absolute 2^-25 (of 2^14) below that.
+__device__ __forceinline__ float rowpair_absmax(const float4& v) {
+    const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
+}
+// a += m * e on two packed fp32 lanes per instruction (FFMA2, sm_100); bit-identical to four fmaf
+__device__ __forceinline__ void fma4(float4& a, float m, const float4& e) {
+    const float2 mm = make_float2(m, m);
+    const float2 lo = __ffma2_rn(mm, make_float2(e.x, e.y), make_float2(a.x, a.y));
+    const float2 hi = __ffma2_rn(mm, make_float2(e.z, e.w), make_float2(a.z, a.w));
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 // one row of the A operand: v (4 columns of this thread) scaled by a per-row power of two, hi | lo planes
 __device__ __forceinline__ void put_operand_row(unsigned char* Arow, float* sclp, int cg, const float4& v) {
-    const float2 sc = pow2_scale_for_fp16(row_absmax(v));
+    const float2 sc = pow2_scale_for_fp16(rowpair_absmax(v));
     uint2 hi, lo;
     split_h2<PREC_3XTF32>(v.x * sc.x, v.y * sc.x, hi.x, lo.x);
     split_h2<PREC_3XTF32>(v.z * sc.x, v.w * sc.x, hi.y, lo.y);
@@ -228,17 +233,13 @@ htem_fwd_kernel(const __grid_constant__ CUtensorMap tm_eb, const __grid_constant
                     const float4 bv = *reinterpret_cast<const float4*>(bsb + t * D);
                     float4 y;
                     y.x = c.x + bv.x + e[t].x; y.y = c.y + bv.y + e[t].y; y.z = c.z + bv.z + e[t].z; y.w = c.w + bv.w + e[t].w;
-                    const uint32_t nib = (y.x > 0.f ? 1u : 0u) | (y.y > 0.f ? 2u : 0u) | (y.z > 0.f ? 4u : 0u) | (y.w > 0.f ? 8u : 0u);
-                    const uint32_t sh = nib << (4 * (cg & 7));
-                    const int wsel = ((lane >> 4) << 1) | (cg >> 3);
-                    const uint32_t w0 = __reduce_or_sync(0xffffffffu, wsel == 0 ? sh : 0u);
-                    const uint32_t w1 = __reduce_or_sync(0xffffffffu, wsel == 1 ? sh : 0u);
-                    const uint32_t w2 = __reduce_or_sync(0xffffffffu, wsel == 2 ? sh : 0u);
-                    const uint32_t w3 = __reduce_or_sync(0xffffffffu, wsel == 3 ? sh : 0u);
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, y.x > 0.f), b1 = __ballot_sync(0xffffffffu, y.y > 0.f);
+                    const uint32_t b2 = __ballot_sync(0xffffffffu, y.z > 0.f), b3 = __ballot_sync(0xffffffffu, y.w > 0.f);
+                    const uint32_t sel = (lane < 16) ? 0x5410u : 0x7632u;      // low halves = the warp's first row, high = second
                     if (row_ok) {
                         y.x = lrelu(y.x); y.y = lrelu(y.y); y.z = lrelu(y.z); y.w = lrelu(y.w);
                         *reinterpret_cast<float4*>(out + gofs + t * slab) = y;
-                        if (cg == 0) mask[(size_t)(b * T + t) * Npad + n0 + n] = (lane < 16) ? make_uint2(w0, w1) : make_uint2(w2, w3);
+                        if (cg == 0) mask[(size_t)(b * T + t) * Npad + n0 + n] = make_uint2(__byte_perm(b0, b1, sel), __byte_perm(b2, b3, sel));
                     }
                 }
             }
@@ -251,10 +252,10 @@ htem_fwd_kernel(const __grid_constant__ CUtensorMap tm_eb, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const float4 m = *reinterpret_cast<const float4*>(Mrow + t * T + 4 * q);
-                        a.x = fmaf(m.x, e[4 * q].x, a.x); a.y = fmaf(m.x, e[4 * q].y, a.y); a.z = fmaf(m.x, e[4 * q].z, a.z); a.w = fmaf(m.x, e[4 * q].w, a.w);
-                        a.x = fmaf(m.y, e[4 * q + 1].x, a.x); a.y = fmaf(m.y, e[4 * q + 1].y, a.y); a.z = fmaf(m.y, e[4 * q + 1].z, a.z); a.w = fmaf(m.y, e[4 * q + 1].w, a.w);
-                        a.x = fmaf(m.z, e[4 * q + 2].x, a.x); a.y = fmaf(m.z, e[4 * q + 2].y, a.y); a.z = fmaf(m.z, e[4 * q + 2].z, a.z); a.w = fmaf(m.z, e[4 * q + 2].w, a.w);
-                        a.x = fmaf(m.w, e[4 * q + 3].x, a.x); a.y = fmaf(m.w, e[4 * q + 3].y, a.y); a.z = fmaf(m.w, e[4 * q + 3].z, a.z); a.w = fmaf(m.w, e[4 * q + 3].w, a.w);
+                        fma4(a, m.x, e[4 * q]);
+                        fma4(a, m.y, e[4 * q + 1]);
+                        fma4(a, m.z, e[4 * q + 2]);
+                        fma4(a, m.w, e[4 * q + 3]);
                     }
                     if (ret != nullptr && row_ok) *reinterpret_cast<float4*>(ret + gofs + t * slab) = a;
                     put_operand_row(Ab + (size_t)(tt * NC + n) * ROWB, scl + tt * NC + n, cg, a);
@@ -338,10 +339,10 @@ htem_bwd_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const float4 m = *reinterpret_cast<const float4*>(Mrow + t * T + 4 * q);
-                        acc[4 * q].x = fmaf(m.x, dr.x, acc[4 * q].x); acc[4 * q].y = fmaf(m.x, dr.y, acc[4 * q].y); acc[4 * q].z = fmaf(m.x, dr.z, acc[4 * q].z); acc[4 * q].w = fmaf(m.x, dr.w, acc[4 * q].w);
-                        acc[4 * q + 1].x = fmaf(m.y, dr.x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(m.y, dr.y, acc[4 * q + 1].y); acc[4 * q + 1].z = fmaf(m.y, dr.z, acc[4 * q + 1].z); acc[4 * q + 1].w = fmaf(m.y, dr.w, acc[4 * q + 1].w);
-                        acc[4 * q + 2].x = fmaf(m.z, dr.x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(m.z, dr.y, acc[4 * q + 2].y); acc[4 * q + 2].z = fmaf(m.z, dr.z, acc[4 * q + 2].z); acc[4 * q + 2].w = fmaf(m.z, dr.w, acc[4 * q + 2].w);
-                        acc[4 * q + 3].x = fmaf(m.w, dr.x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(m.w, dr.y, acc[4 * q + 3].y); acc[4 * q + 3].z = fmaf(m.w, dr.z, acc[4 * q + 3].z); acc[4 * q + 3].w = fmaf(m.w, dr.w, acc[4 * q + 3].w);
+                        fma4(acc[4 * q], m.x, dr);
+                        fma4(acc[4 * q + 1], m.y, dr);
+                        fma4(acc[4 * q + 2], m.z, dr);
+                        fma4(acc[4 * q + 3], m.w, dr);
                     }
                 }
             }
@@ -353,11 +354,11 @@ htem_bwd_kernel(const __grid_constant__ CUtensorMap tm_go, const __grid_constant
                     const int t = RT * r + tt;
                     float4 dy = *reinterpret_cast<const float4*>(land + ((r * RT + tt) * NC + n) * D + 4 * cg);
                     const uint2 mw = msk[(r * RT + tt) * NC + n];
-                    const uint32_t bits = ((cg < 8 ? mw.x : mw.y) >> (4 * (cg & 7))) & 15u;
-                    dy.x = (bits & 1u) ? dy.x : kSlope * dy.x;
-                    dy.y = (bits & 2u) ? dy.y : kSlope * dy.y;
-                    dy.z = (bits & 4u) ? dy.z : kSlope * dy.z;
-                    dy.w = (bits & 8u) ? dy.w : kSlope * dy.w;
+                    const uint32_t mx = mw.x >> cg, my = mw.y >> cg;           // bit 16*(c & 3) + (c >> 2) of the row's word
+                    dy.x = (mx & 1u) ? dy.x : kSlope * dy.x;
+                    dy.y = (mx & 0x10000u) ? dy.y : kSlope * dy.y;
+                    dy.z = (my & 1u) ? dy.z : kSlope * dy.z;
+                    dy.w = (my & 0x10000u) ? dy.w : kSlope * dy.w;
                     acc[t].x += dy.x; acc[t].y += dy.y; acc[t].z += dy.z; acc[t].w += dy.w;
                     put_operand_row(Ab + (size_t)(tt * NC + n) * ROWB, scl + tt * NC + n, cg, dy);
                 }

@@ -37,7 +37,8 @@ __device__ __forceinline__ void stage_tile(unsigned char* tile, const float* bas
     }
 }
 
-template <int PREC>
+// DM_ONLY: only the dM tile (the side-stream half of the fused hyperTem backward, csrc/htem_fused.cu); dx_io / M unused
+template <int PREC, bool DM_ONLY>
 __global__ void __launch_bounds__(256, TMIX_MINB)
 tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ M,
                 float* __restrict__ dx_io, float* __restrict__ dM_part, int B, int N, int bps) {
@@ -60,9 +61,9 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
     const bool r1ok = g + 8 < T;
 
     // ---- A fragments of the mix: A[m = s][k = tt] = M[n][tt][s], one power-of-two scale per node
-    uint32_t mh[4], ml[4];
-    float m_inv;
-    {
+    uint32_t mh[4] = {0u, 0u, 0u, 0u}, ml[4] = {0u, 0u, 0u, 0u};
+    float m_inv = 1.f;
+    if (!DM_ONLY) {
         const float* Mn = M + (size_t)n * T * T;
         float a[8];
 #pragma unroll
@@ -98,10 +99,12 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
         cp_async_commit();
         // the dx tile this warp will update: same chunk mapping, straight to registers (overlaps the staging)
         float4 dxv[6];
+        if (!DM_ONLY) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
-            dxv[k] = *reinterpret_cast<const float4*>(dxp + (size_t)r * slab + ch * 4);
+            for (int k = 0; k < 6; ++k) {
+                const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+                dxv[k] = *reinterpret_cast<const float4*>(dxp + (size_t)r * slab + ch * 4);
+            }
         }
         cp_async_wait_group<0>();
         __syncwarp();
@@ -154,6 +157,7 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
             }
         }
         __syncwarp();                               // x tile consumed: its slots become the staging area of the update
+        if (DM_ONLY) continue;
         // ---- update tile = M^T dy : B[k = tt][n = column] = dy[tt][8j + g]  (conflict-free scalar reads of the fp32 tile)
         const float un = sc.y * m_inv;
 #pragma unroll
@@ -221,13 +225,27 @@ extern "C" int gptst_tmix_bwd(const float* dy, const float* x, const float* M, f
     const size_t smem = (size_t)8 * tm2::WARP_BYTES;
     cudaError_t e;
     if (prec == 3) {
-        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_3XTF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_3XTF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        tm2::tmix_bwd_kernel<PREC_3XTF32><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
+        tm2::tmix_bwd_kernel<PREC_3XTF32, false><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
     } else {
-        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_TF32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        tm2::tmix_bwd_kernel<PREC_TF32><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
+        tm2::tmix_bwd_kernel<PREC_TF32, false><<<grid, 256, smem, st>>>(dy, x, M, dx_io, dM_part, B, N, bps);
     }
+    return (int)cudaGetLastError();
+}
+
+// dM only (side-stream half of the fused hyperTem backward): dM_part[split][n][t][s] = sum over the split's batches and the
+// 64 columns of dret[b,t,n,:] x[b,s,n,:].  splits = gptst_tmix_bwd_splits(B, N).
+extern "C" int gptst_tmix_dM2(const float* dret, const float* x, float* dM_part, int B, int T, int N, int D, int splits, void* stream) {
+    if (!dret || !x || !dM_part || B <= 0 || N <= 0 || splits <= 0) return -1;
+    if (T != tm2::T || D != tm2::D) return -2;
+    const int bps = (B + splits - 1) / splits;
+    dim3 grid((N + 7) / 8, splits);
+    const size_t smem = (size_t)8 * tm2::WARP_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(tm2::tmix_bwd_kernel<PREC_3XTF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    tm2::tmix_bwd_kernel<PREC_3XTF32, true><<<grid, 256, smem, (cudaStream_t)stream>>>(dret, x, nullptr, nullptr, dM_part, B, N, bps);
     return (int)cudaGetLastError();
 }

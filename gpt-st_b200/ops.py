@@ -320,13 +320,132 @@ class _HyperTemCore(torch.autograd.Function):
         return deb, dM_part, dW.view(B, T, D, D), db.view(B, T, D), None
 
 
+# ---------------------------------------------------------------------------------------------------
+# fused hyperTem (csrc/htem_fused.cu): ONE TMA-fed kernel per direction on the main chain.  The parameter-side gradients
+# (dW_bt = ret^T dy, db_bt, dM_n = dret . eb) are not needed by anything on the main chain, so they belong to a second
+# autograd node, `_HyperTemParams`, that sits between the table generators and the block.  Autograd runs a node's backward
+# on the stream its forward ran on: when `hyperTem.tables` builds the node on the block's table stream, those two
+# kernels run there, overlapped with the next block's backward.  The block hands them their inputs through a mailbox and
+# returns stride-0 zero placeholders as the "gradients" of the node's outputs (autograd only needs the dependency).
+# ---------------------------------------------------------------------------------------------------
+def hypertem_fused_enabled(D: int, T: int, prec: int) -> bool:
+    """Fused kernels cover D = 64, T = 12, three-term split (GPTST_B200_HTEM=split selects the unfused pair)."""
+    return D == 64 and T == 12 and prec == PREC_3XTF32 and os.environ.get("GPTST_B200_HTEM", "fused") == "fused"
+
+
+_zero_scalars = {}
+
+
+def _zero_like_shape(shape, device):
+    """Stride-0 zero tensor of `shape` (placeholder gradient; nobody reads its values)."""
+    z = _zero_scalars.get(device)
+    if z is None:
+        z = _zero_scalars[device] = torch.zeros((), device=device, dtype=torch.float32)
+    return z.expand(tuple(shape))
+
+
+class _HyperTemParams(torch.autograd.Function):
+    """(Mn, W, bias) -> the same three tensors; the forward also packs W into the fragment-ordered fp16 tables of the fused
+    kernels (mailbox['wf'], ['wb']).  The backward ignores its incoming placeholders and computes the real dM_n, dW_bt, db_bt
+    from what the block's backward left in the mailbox."""
+
+    @staticmethod
+    def forward(ctx, mb, Mn, W, bias):
+        Mn, W, bias = Mn.contiguous(), W.contiguous(), bias.contiguous()
+        _chk(Mn, W, bias)
+        L = _lib.lib()
+        G = W.shape[0] * W.shape[1]
+        nbytes = L.gptst_hypertem_wfrag_bytes(G)
+        wf = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+        wb = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
+        _lib.check(L.gptst_hypertem_pack_w(_p(W), _p(wf), _p(wb), G, _stream()), "gptst_hypertem_pack_w")
+        mb["wf"], mb["wb"], mb["stream"] = wf, wb, torch.cuda.current_stream()
+        ctx.mb = mb
+        return Mn.view_as(Mn), W.view_as(W), bias.view_as(bias)
+
+    @staticmethod
+    def backward(ctx, _gM, _gW, _gb):
+        mb = ctx.mb
+        dout, mask, ret, dret, eb = (mb.pop(k) for k in ("dout", "mask", "ret", "dret", "eb"))
+        B, T, N, D = eb.shape
+        L = _lib.lib()
+        G = B * T
+        splits = L.gptst_gproj_splits(G, N, D)
+        dWp = torch.empty((splits, B, T, D, D), device=eb.device, dtype=torch.float32)
+        dbp = torch.empty((splits, B, T, D), device=eb.device, dtype=torch.float32)
+        _lib.check(L.gptst_hypertem_dw(_p(dout), _p(mask), _p(ret), _p(dWp), _p(dbp), B, T, N, D, mask.shape[1], splits, _stream()),
+                   "gptst_hypertem_dw")
+        sp = L.gptst_tmix_bwd_splits(B, N)
+        dMp = torch.empty((sp, N, T, T), device=eb.device, dtype=torch.float32)
+        _lib.check(L.gptst_tmix_dM2(_p(dret), _p(eb), _p(dMp), B, T, N, D, sp, _stream()), "gptst_tmix_dM2")
+        dM, dW, db = sum_partials(dMp, dWp, dbp)
+        return None, dM, dW, db
+
+
+class _HyperTemFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eb, Mn, W, bias, mb):
+        eb, Mn, bias = eb.contiguous(), Mn.contiguous(), bias.contiguous()
+        _chk(eb, Mn, bias)
+        B, T, N, D = eb.shape
+        L = _lib.lib()
+        npad = (N + 15) // 16 * 16
+        out = torch.empty_like(eb)
+        # ret = M_n o eb is only kept for the side-stream dW kernel; a forward without parameter gradients skips the store
+        ret = torch.empty_like(eb) if any(ctx.needs_input_grad[1:4]) else None
+        mask = torch.empty((B * T, npad, 2), device=eb.device, dtype=torch.int32)
+        _lib.check(L.gptst_hypertem_fwd(_p(eb), _p(Mn), _p(mb["wf"]), _p(bias), _p(out), _p(mask), _p(ret), B, T, N, D, _stream()),
+                   "gptst_hypertem_fwd")
+        ctx.save_for_backward(eb, Mn, ret, mask, mb["wb"])
+        ctx.mb = mb
+        ctx.want_params = ret is not None
+        ctx.shapes = (Mn.shape, W.shape, bias.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eb, Mn, ret, mask, wb = ctx.saved_tensors
+        mb = ctx.mb
+        dout = dout.contiguous()
+        B, T, N, D = eb.shape
+        deb = torch.empty_like(eb)
+        dret = torch.empty_like(eb) if ctx.want_params else None
+        _lib.check(_lib.lib().gptst_hypertem_bwd(_p(dout), _p(mask), _p(Mn), _p(wb), _p(deb), _p(dret), B, T, N, D, _stream()),
+                   "gptst_hypertem_bwd")
+        if not ctx.want_params:
+            return deb, None, None, None, None
+        side = mb["stream"]
+        if side != torch.cuda.current_stream():
+            for t in (dout, mask, ret, dret, eb):
+                t.record_stream(side)
+        mb.update(dout=dout, mask=mask, ret=ret, dret=dret, eb=eb)
+        sM, sW, sb = ctx.shapes
+        dev = eb.device
+        return deb, _zero_like_shape(sM, dev), _zero_like_shape(sW, dev), _zero_like_shape(sb, dev), None
+
+
+def hypertem_params(Mn, W, bias):
+    """Parameter-side node of the fused hyperTem block: call it where the tables are produced (their stream is where the
+    parameter gradients will be computed).  Returns (Mn, W, bias, mailbox) for `hypertem_fused`."""
+    mb = {}
+    Mn2, W2, b2 = _HyperTemParams.apply(mb, Mn, W, bias)
+    return Mn2, W2, b2, mb
+
+
+def hypertem_fused(eb, Mn2, W2, b2, mb):
+    return _HyperTemFused.apply(eb, Mn2, W2, b2, mb)
+
+
 def hypertem_core(eb, Mn, W, bias, prec=None):
     """eb (B,T,N,D); Mn (N,T,T) = A_n^T A_n, or already expanded to (P,N,T,T) by `expand_partials`; W (B,T,D,D); bias (B,T,D)."""
+    prec = default_precision() if prec is None else prec
     if Mn.dim() == 3:
         if not eb.is_cuda:
             raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
+        if hypertem_fused_enabled(eb.shape[3], eb.shape[1], prec):
+            return hypertem_fused(eb, *hypertem_params(Mn, W, bias))
         Mn = expand_partials(Mn, hypertem_partial_count(eb.shape[0], eb.shape[2], eb.shape[3]))
-    return _HyperTemCore.apply(eb, Mn, W, bias, default_precision() if prec is None else prec)
+    return _HyperTemCore.apply(eb, Mn, W, bias, prec)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -56,6 +56,27 @@ int gptst_tmix_bwd_splits(int B, int N);
 int gptst_tmix_bwd(const float* dy, const float* x, const float* M, float* dx_io, float* dM_part, int B, int T, int N, int D,
                    int prec, int splits, void* stream);
 
+/* ---- fused hyperTem block, GPTST.py:154-163 (D = 64, T = 12): one TMA-fed persistent kernel per direction --------------------
+ * Replaces gptst_tmix + gptst_gproj_fwd (forward) and gptst_gproj_bwd + gptst_tmix_bwd (backward) on the main chain.
+ *   pack_w : W (G = B*T, 64, 64) fp32 [in][out] -> fragment-ordered fp16 hi/lo tables, wf for the forward (ret W), wb for the
+ *            backward (dy W^T); gptst_hypertem_wfrag_bytes(G) bytes each; either may be NULL.
+ *   fwd    : out = LReLU((M_n o eb) W_bt + bias_bt + eb);  mask = sign words of out, (B*T, Npad, 2) uint32 with Npad = N rounded
+ *            up to 16 and bit 16*(c & 3) + (c >> 2) of a row's 64 bits = out[c] > 0;  ret (may be NULL) = M_n o eb.
+ *   bwd    : deb = dy + M_n^T o (dy W_bt^T) with dy = dOut . LReLU'(mask);  dret (may be NULL) = dy W_bt^T.
+ *   dw     : dW_part[s][b,t] = partial of ret_bt^T dy_bt, dbias_part[s][b,t] = partial of sum_n dy_bt  (s < gptst_gproj_splits(B*T, N, 64))
+ *   tmix_dM2: dM_part[s][n][t][t'] = partial of sum_{b,j} dret[b,t,n,j] eb[b,t',n,j]                  (s < gptst_tmix_bwd_splits(B, N))
+ * The last two are the parameter-side gradients (G_bt, sigma_bt, dM_n); nothing on the main chain reads them. */
+long gptst_hypertem_wfrag_bytes(int G);
+int gptst_hypertem_mask_pad_rows(void);
+int gptst_hypertem_pack_w(const float* W, void* wf, void* wb, int G, void* stream);
+int gptst_hypertem_fwd(const float* eb, const float* Mn, const void* wfrag, const float* bias, float* out, void* mask, float* ret, int B,
+                       int T, int N, int D, void* stream);
+int gptst_hypertem_bwd(const float* dout, const void* mask, const float* Mn, const void* wfrag_t, float* deb, float* dret, int B, int T,
+                       int N, int D, void* stream);
+int gptst_hypertem_dw(const float* dout, const void* mask, const float* ret, float* dW_part, float* dbias_part, int B, int T, int N,
+                      int D, int mask_rows, int splits, void* stream);
+int gptst_tmix_dM2(const float* dret, const float* x, float* dM_part, int B, int T, int N, int D, int splits, void* stream);
+
 /* ---- cap: intra-cluster routing, GPTST.py:102-123 ----------------------------------------------------
  * P = squash(x Wp^T + bp); R routing iterations on (P, dadj); c = softmax_H(b + dadj) -> c (B,T,H,N); s = c P.
  * D = 64, N <= 256: one CTA per (b,t) slab, one warp per 16 nodes, fp16-split tensor-core contractions

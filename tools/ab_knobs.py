@@ -8,9 +8,11 @@ import bench
 from gptst_b200.GPTST import GPTST_Model
 from gptst_b200.train import PretrainStep
 
-KNOBS = ("GPTST_B200_OPT_PREFETCH", "GPTST_B200_SCORER_PRIO", "GPTST_B200_EXPAND")
+KNOBS = ("GPTST_B200_OPT_PREFETCH", "GPTST_B200_SCORER_PRIO", "GPTST_B200_EXPAND", "GPTST_B200_HTEM", "GPTST_B200_CAP")
 VARIANTS = [{}, {"GPTST_B200_OPT_PREFETCH": "1"}, {"GPTST_B200_SCORER_PRIO": "low"},
             {"GPTST_B200_OPT_PREFETCH": "1", "GPTST_B200_SCORER_PRIO": "low"}, {"GPTST_B200_EXPAND": "native"}]
+if len(sys.argv) > 1:          # python tools/ab_knobs.py '[{}, {"GPTST_B200_HTEM": "split"}]'
+    VARIANTS = json.loads(sys.argv[1])
 N, D, B = bench.WORKLOADS["pems08"]
 g = torch.Generator().manual_seed(100)
 host = [torch.randn(B, 12, N, 3, generator=g).pin_memory() for _ in range(4)]
@@ -38,11 +40,10 @@ for v in VARIANTS:
     step = PretrainStep(model, lr=3e-3, max_grad_norm=5.0, loss="probe")
     random.seed(1234)
     torch.manual_seed(1234)
-    for i in range(6):
-        step(res[i % 4], 200)
+    first = [float(step(res[i % 4], 200)) for i in range(6)]
     r = [timed(step, 30, False) for _ in range(3)]
     e = [timed(step, 30, True) for _ in range(2)]
     print(json.dumps({"env": v, "ms_min": min(x[0] for x in r), "ms_med": statistics.median(x[0] for x in r),
-                      "e2e_ms_min": min(x[0] for x in e), "loss_after_96": r[-1][1], "loss_after_156": e[-1][1]}), flush=True)
+                      "e2e_ms_min": min(x[0] for x in e), "first_losses": first, "loss_after_96": r[-1][1], "loss_after_156": e[-1][1]}), flush=True)
     del step, model
     torch.cuda.empty_cache()

@@ -51,7 +51,8 @@ __global__ void mask_check(const float* y, const uint2* mask, int BT, int N, int
         const int c = (int)(i & 63);
         const size_t bt = r / N, n = r % N;
         const uint2 m = mask[bt * Npad + n];
-        const unsigned bit = ((c < 32 ? m.x : m.y) >> (c & 31)) & 1u;
+        const int p = 16 * (c & 3) + (c >> 2);          // ballot order of the fused kernels
+        const unsigned bit = ((p < 32 ? m.x : m.y) >> (p & 31)) & 1u;
         if (bit != (y[i] > 0.f ? 1u : 0u)) atomicAdd(bad, 1u);
     }
 }
