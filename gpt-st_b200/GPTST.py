@@ -10,10 +10,11 @@ parameters in the same order), same ``forward(source, label, batch_seen=None, ep
     cap       (ref :79-141)    -> ops.cap_core        (routing, inter-cluster hop, node-adaptive GCN)
     MLP_RL    (ref :6-34)      -> ops.node_adaptive_proj / ops.time_adaptive_proj
 
-What stays in PyTorch: the seven tiny time-embedding MLPs (ref :187-219, O(B*T) work), the
-parameter-sized contractions that build the adaptive weight tables / incidence logits, the skinny
-input/output linears and the mask bookkeeping (same ``rand_like`` / ``sort`` / ``random.shuffle`` draws as the
-reference, so masks are bit-identical for equal seeds on the same device).
+Everything (B,T,N,*)-sized runs in libgptst_b200 kernels: the fused hyperTem blocks (csrc/htem_fused.cu), the cap chain, the
+scorer, the time-embedding MLPs and low-rank table generators (csrc/small_ops.cu), the mask construction (csrc/mask.cu: same
+``rand_like`` / ``random.shuffle`` draws as the reference, so masks are bit-identical for equal seeds on the same device), the
+input / output projections and the loss.  PyTorch keeps the module tree, autograd bookkeeping, streams and a few elementwise
+glue ops ((1 - mask), the masked fill).
 
 The model never touches ``'cuda:0'`` literally: it follows the device of its inputs, so one process per
 GPU (LOCAL_RANK) works for data parallel training.
@@ -314,6 +315,9 @@ class Hypergraph_encoder(nn.Module):
         self.label_c_override = None
         # graph replay hook: int64 device vector [order, adaptive_num, random_num] (see mask_plan)
         self.plan_override = None
+        # hook for exact parity tests: {"u1": ..., "u2": ...} device vectors used INSTEAD of the torch.rand_like draws
+        # (ref :316 / :389,:400); static buffers, so a captured step can be fed the oracle's draws replay by replay
+        self.draws_override = None
         self._k_cache = {}
 
     # -- mask scorer (both phases), ref :326-332 / :338-343
@@ -377,8 +381,11 @@ class Hypergraph_encoder(nn.Module):
         else:
             plan = self.mask_plan(n, epoch).to(dev)
         # the same two draws, in the same order, as the reference (:389, :400)
-        u1 = torch.rand_like(source[..., 0:1].reshape(-1))
-        u2 = torch.rand_like(source[..., 0:1].reshape(-1))
+        if self.draws_override is not None:
+            u1, u2 = self.draws_override["u1"], self.draws_override["u2"]
+        else:
+            u1 = torch.rand_like(source[..., 0:1].reshape(-1))
+            u2 = torch.rand_like(source[..., 0:1].reshape(-1))
         # label = arg-max class (== sort(descending)[..., 0] of ref :344-345 up to exact ties) unless a test injects labels
         final = ops.mask_adaptive(prob, self.label_c_override, plan, u1, u2, i0, self.ada_type == "all")
         return final.reshape(prob.shape[:-1] + (i0,))
@@ -438,7 +445,7 @@ class Hypergraph_encoder(nn.Module):
             return enc
         score = pro.get("score") if pro is not None else None     # (prob, event) computed on a side stream
         if epoch <= self.change_epoch:
-            u = torch.rand_like(flow.reshape(-1))
+            u = self.draws_override["u1"] if self.draws_override is not None else torch.rand_like(flow.reshape(-1))
             k = int(u.shape[0] * self.mask_ratio)
             kd = self._k_cache.get((k, u.device))
             if kd is None:

@@ -33,7 +33,9 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(const float* __restri
             g = (e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f)) * m;
             cnt += 1.f;
         } else {                               // mask_mae
-            const float p = (ov * std_ + mean) * m, t = (x * std_ + mean) * m;
+            // the reference's inverse z-score is two rounded fp32 ops (lib/normalization.py: data * std + mean), NOT a fused
+            // multiply-add: whether a gap cell (true == 0 after the transform) passes `t > thr` depends on that last bit
+            const float p = __fadd_rn(__fmul_rn(ov, std_), mean) * m, t = __fadd_rn(__fmul_rn(x, std_), mean) * m;
             const bool sel = t > thr;
             e = sel ? (t - p) : 0.f;
             g = sel ? ((e > 0.f ? -1.f : (e < 0.f ? 1.f : 0.f)) * std_ * m) : 0.f;

@@ -2,19 +2,21 @@
 // reference BasicTrainer.py:94-97: clip_grad_norm_(max_grad_norm) then Adam.step()).
 //
 // torch runs this as ~16 foreach launches over 135 small tensors (0.8 ms of a 6.3 ms step on B200, nothing to overlap
-// with).  Here: a device table of (param, grad, exp_avg, exp_avg_sq, numel, first_step) entries plus a block map, and
+// with).  Here: a device table of (param, grad, exp_avg, exp_avg_sq, numel, step counter) entries plus a block map, and
 // two launches: (1) per-block sum of squares of the gradients (+ the global step counter), (2) every block re-derives the
 // global norm from the partials (fixed order, deterministic), forms the clip coefficient and applies Adam to its chunk.
 // Math follows torch.optim.Adam (amsgrad=False, weight_decay=0): m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;
-// p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps), with t counted per parameter from its first gradient.
+// p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps), with t counted PER PARAMETER ON THE DEVICE (one int32 each, bumped by the
+// first launch): a parameter that gets its first gradient after thousands of graph replays still starts at t = 1, as
+// torch.optim.Adam's per-parameter state['step'] does.
 #include "common.cuh"
 
 namespace gptst {
 
 constexpr int kOptChunk = 2048;   // elements per block
 
-struct OptEntry {     // 6 x int64 per tensor, filled by the host side (gptst_b200/optim.py)
-    long long p, g, m, v, n, first_step;
+struct OptEntry {     // 6 x int64 per tensor, filled by the host side (gptst_b200/optim.py); t = device int32* step counter
+    long long p, g, m, v, n, t;
 };
 
 __global__ void __launch_bounds__(256) opt_sqnorm_kernel(const OptEntry* __restrict__ tab, const int2* __restrict__ blocks,
@@ -35,6 +37,7 @@ __global__ void __launch_bounds__(256) opt_sqnorm_kernel(const OptEntry* __restr
         for (int w = 0; w < 8; ++w) t += red[w];
         partial[blockIdx.x] = t;
         if (blockIdx.x == 0) step[0] += 1;
+        if (bm.y == 0) *reinterpret_cast<int*>(e.t) += 1;            // this tensor's own step count (read by the second launch)
     }
 }
 
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(256) opt_adam_kernel(const OptEntry* __restric
     const float coef = coef_s, lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
     const int2 bm = blocks[blockIdx.x];
     const OptEntry e = tab[bm.x];
-    const float t = (float)(step[0] - (int)e.first_step);
+    const float t = (float)(*reinterpret_cast<const int*>(e.t));
     const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
     const float step_size = lr / bc1, rs2 = rsqrtf(bc2);
     float* p = reinterpret_cast<float*>(e.p);

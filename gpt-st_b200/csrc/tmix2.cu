@@ -119,6 +119,16 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         const float2 sc = pow2_scale_for_fp16(mx);
+        // x is an activation of any magnitude: its tile gets a power-of-two scale of its own (exact, undone below)
+        float mxx = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int id = lane + 32 * k, r = id >> 4, ch = id & 15;
+            const float4 v = *reinterpret_cast<const float4*>(Tx + (size_t)r * ROWB + ch * 16);
+            mxx = fmaxf(mxx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+        mxx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mxx)));
+        const float2 sx = pow2_scale_for_fp16(mxx);
         // ---- dM tile += dy x^T   (both operands by ldmatrix from the fp32 tiles: same k permutation on both sides)
         {
             float th[2][4], tl[2][4];
@@ -136,11 +146,11 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
                 split_h2<PREC>(__uint_as_float(f[0]) * sc.x, __uint_as_float(f[1]) * sc.x, ah[1], al[1]);
                 split_h2<PREC>(__uint_as_float(f[2]) * sc.x, __uint_as_float(f[3]) * sc.x, ah[3], al[3]);
                 ldsm_x4(f, baddr);                  // x rows s = 0..7  -> B fragments of tile 0
-                split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), bh[0], bl[0]);
-                split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), bh[1], bl[1]);
+                split_h2<PREC>(__uint_as_float(f[0]) * sx.x, __uint_as_float(f[1]) * sx.x, bh[0], bl[0]);
+                split_h2<PREC>(__uint_as_float(f[2]) * sx.x, __uint_as_float(f[3]) * sx.x, bh[1], bl[1]);
                 ldsm_x4(f, baddr + 8 * ROWB);       // x rows s = 8..15 -> tile 1
-                split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), bh[2], bl[2]);
-                split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), bh[3], bl[3]);
+                split_h2<PREC>(__uint_as_float(f[0]) * sx.x, __uint_as_float(f[1]) * sx.x, bh[2], bl[2]);
+                split_h2<PREC>(__uint_as_float(f[2]) * sx.x, __uint_as_float(f[3]) * sx.x, bh[3], bl[3]);
                 if (PREC == PREC_3XTF32) {
                     mma_f16(tl[0], al, bh[0], bh[1]);
                     mma_f16(tl[1], al, bh[2], bh[3]);
@@ -152,8 +162,8 @@ tmix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                dm[0][i] = fmaf(th[0][i] + tl[0][i], sc.y, dm[0][i]);
-                dm[1][i] = fmaf(th[1][i] + tl[1][i], sc.y, dm[1][i]);
+                dm[0][i] = fmaf(th[0][i] + tl[0][i], sc.y * sx.y, dm[0][i]);
+                dm[1][i] = fmaf(th[1][i] + tl[1][i], sc.y * sx.y, dm[1][i]);
             }
         }
         __syncwarp();                               // x tile consumed: its slots become the staging area of the update

@@ -24,9 +24,10 @@ def masked_mae(pred, true, mask, mean: float, std: float, mask_value=0.0):
     return (t - p).abs().mean()
 
 
-def pretrain_loss(outs, source, epoch: int, change_epoch: int, mean: float, std: float, output_dim: int = 1):
+def pretrain_loss(outs, source, epoch: int, change_epoch: int, mean: float, std: float, output_dim: int = 1,
+                  mask_value: float = 0.0):
     flow_out, _, inv_mask, prob, hs1 = outs
-    loss = masked_mae(flow_out, source[..., :output_dim], inv_mask, mean, std, 0.0)
+    loss = masked_mae(flow_out, source[..., :output_dim], inv_mask, mean, std, mask_value)
     if epoch > change_epoch:
         loss = loss + 0.1 * kl_sum(prob, hs1)
     return loss
@@ -51,9 +52,11 @@ def masked_mae_syncfree(pred, true, mask, mean: float, std: float, mask_value=0.
     return ((t - p).abs() * sel).sum() / sel.sum()
 
 
-def pretrain_loss_syncfree(outs, source, epoch: int, change_epoch: int, mean: float, std: float, output_dim: int = 1):
+def pretrain_loss_syncfree(outs, source, epoch: int, change_epoch: int, mean: float, std: float, output_dim: int = 1,
+                           mask_value: float = 0.0):
+    """mask_value = args.mape_thresh of the reference (Run.py:116-122: 0.0 for PEMS08 / METR_LA, 0.001 for NYC_BIKE / NYC_TAXI)."""
     flow_out, _, inv_mask, prob, hs1 = outs
-    loss = masked_mae_syncfree(flow_out, source[..., :output_dim], inv_mask, mean, std, 0.0)
+    loss = masked_mae_syncfree(flow_out, source[..., :output_dim], inv_mask, mean, std, mask_value)
     if epoch > change_epoch:
         loss = loss + 0.1 * kl_sum(prob, hs1)
     return loss

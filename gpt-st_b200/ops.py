@@ -50,6 +50,9 @@ def _chk(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
+        if t.device.index != torch.cuda.current_device():
+            raise RuntimeError(f"gptst_b200 ops launch on the CURRENT device's stream: tensor on {t.device}, current device "
+                               f"cuda:{torch.cuda.current_device()} (wrap the call in torch.cuda.device(t.device))")
         if t.dtype != torch.float32:
             raise RuntimeError(f"gptst_b200 ops are fp32, got {t.dtype}")
         if not t.is_contiguous():
@@ -932,7 +935,7 @@ class _FusedLoss(torch.autograd.Function):
         st = _stream()
         _count(1)
         d_o = torch.empty_like(o)
-        d_p = torch.empty_like(prob) if kl_w != 0.0 else None
+        d_p = torch.empty_like(prob) if kl_w != 0.0 else None          # (prob is None without the KL term)
         part = torch.empty(3 * L.gptst_loss_parts(), device=o.device, dtype=torch.float32)
         out = torch.empty(3, device=o.device, dtype=torch.float32)
         pc = prob.contiguous() if kl_w != 0.0 else None
@@ -954,10 +957,13 @@ class _FusedLoss(torch.autograd.Function):
 def fused_probe_loss(outs, source, use_kl: bool, kl_weight: float = 0.1):
     """mean|(o - x)*mask| (+ kl_weight * KL(sum)) -- one fused kernel pair; returns the scalar loss."""
     flow_out, _, inv_mask, prob, hs = outs
-    return _FusedLoss.apply(flow_out, prob, source, inv_mask, hs, 0, 0.0, 1.0, 0.0, kl_weight if use_kl else 0.0)[0]
+    # without the KL term the scorer is NOT part of the loss graph (BasicTrainer.py:84-88): its parameters must end the step with
+    # grad None -- a zero gradient would make Adam create state and count steps for them during the random-mask phase
+    return _FusedLoss.apply(flow_out, prob if use_kl else None, source, inv_mask, hs, 0, 0.0, 1.0, 0.0, kl_weight if use_kl else 0.0)[0]
 
 
 def fused_mask_mae_loss(outs, source, use_kl: bool, mean: float, std: float, mask_value: float = 0.0, kl_weight: float = 0.1):
     """Reference training loss (Run.py:91-101 + BasicTrainer.py:84-86) as one fused kernel pair."""
     flow_out, _, inv_mask, prob, hs = outs
-    return _FusedLoss.apply(flow_out, prob, source, inv_mask, hs, 1, mean, std, mask_value, kl_weight if use_kl else 0.0)[0]
+    return _FusedLoss.apply(flow_out, prob if use_kl else None, source, inv_mask, hs, 1, mean, std, mask_value,
+                            kl_weight if use_kl else 0.0)[0]

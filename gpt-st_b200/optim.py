@@ -2,7 +2,8 @@
 
 Drop-in for the reference's ``clip_grad_norm_(model.parameters(), max_grad_norm); optimizer.step()``
 (BasicTrainer.py:94-97, Adam created at Run.py:134).  Parameters whose ``.grad`` is None are skipped exactly as
-torch.optim.Adam skips them, and their step count starts at their first gradient.  CUDA-graph safe: the pointer table
+torch.optim.Adam skips them; every parameter has its own step counter ON THE DEVICE (bumped by the kernel), so a parameter that
+gets its first gradient after any number of CUDA-graph replays starts at t = 1 like torch.optim.Adam's per-parameter state.  CUDA-graph safe: the pointer table
 travels through a pinned host buffer (a memcpy node that re-reads the same, still valid, addresses at replay).
 """
 from __future__ import annotations
@@ -25,9 +26,8 @@ class FusedAdamClip:
         if dev.type != "cuda":
             raise RuntimeError("FusedAdamClip needs CUDA parameters (no CPU fallback)")
         self.device = dev
-        self.state = {}                                    # param -> (exp_avg, exp_avg_sq, first_step)
+        self.state = {}                                    # param -> (exp_avg, exp_avg_sq, int32 device step counter)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.host_steps = 0                                # mirror of step_count for assigning first_step
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps, max_grad_norm if max_grad_norm else 0.0],
                                   dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -53,29 +53,37 @@ class FusedAdamClip:
         for idx, p in enumerate(live):
             if p not in self.state:
                 self.state[p] = (torch.zeros_like(p, memory_format=torch.contiguous_format),
-                                 torch.zeros_like(p, memory_format=torch.contiguous_format), self.host_steps)
-            m, v, first = self.state[p]
+                                 torch.zeros_like(p, memory_format=torch.contiguous_format),
+                                 torch.zeros(1, dtype=torch.int32, device=p.device))
+            m, v, tcount = self.state[p]
             g = p.grad
             if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
             n = p.numel()
-            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, first])
+            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, tcount.data_ptr()])
             bmap += [[idx, c] for c in range((n + self.chunk - 1) // self.chunk)]
         capturing = torch.cuda.is_current_stream_capturing()
         if capturing:
             self._captures += 1
-        key = (len(live), self._captures if capturing else 0)      # a captured graph owns its table (never rewritten later)
+        # one entry per LIVE SET (the block map depends on which tensors are live, not only on how many); a captured graph owns
+        # its table (never rewritten later)
+        key = (tuple(id(p) for p in live), self._captures if capturing else 0)
         ent = self._tables.get(key)
-        if ent is None or ent[0].shape[0] != len(rows) or ent[4] != len(bmap):
+        if ent is None:
             pinned = torch.empty((len(rows), 6), dtype=torch.int64).pin_memory()
             bpin = torch.tensor(bmap, dtype=torch.int32).pin_memory()
             bdev = torch.empty((len(bmap), 2), dtype=torch.int32, device=self.device)
             bdev.copy_(bpin, non_blocking=True)                     # pinned -> device: legal inside a capture
             ent = [pinned, torch.empty((len(rows), 6), dtype=torch.int64, device=self.device), bdev,
-                   torch.empty(len(bmap), dtype=torch.float32, device=self.device), len(bmap), bpin]
+                   torch.empty(len(bmap), dtype=torch.float32, device=self.device), len(bmap), bpin, None]
             self._tables[key] = ent
+        elif ent[6] is not None:
+            ent[6].synchronize()                                    # eager mode: the previous step's H2D copy has read the pinned rows
         ent[0].copy_(torch.tensor(rows, dtype=torch.int64))
         ent[1].copy_(ent[0], non_blocking=True)
+        if not capturing:
+            ent[6] = torch.cuda.Event()
+            ent[6].record()
         return ent
 
     def prefetch_tables(self) -> None:
@@ -110,13 +118,14 @@ class FusedAdamClip:
         for idx, p in enumerate(live):
             if p not in self.state:
                 self.state[p] = (torch.zeros_like(p, memory_format=torch.contiguous_format),
-                                 torch.zeros_like(p, memory_format=torch.contiguous_format), self.host_steps)
-            m, v, first = self.state[p]
+                                 torch.zeros_like(p, memory_format=torch.contiguous_format),
+                                 torch.zeros(1, dtype=torch.int32, device=p.device))
+            m, v, tcount = self.state[p]
             g = p.grad
             if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
             n = p.numel()
-            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, first])
+            rows.append([p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, tcount.data_ptr()])
             bmap += [[idx, c] for c in range((n + self.chunk - 1) // self.chunk)]
         pinned[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))          # host writes: the captured copies read them at replay
         bpin[:len(bmap)].copy_(torch.tensor(bmap, dtype=torch.int32))
@@ -124,7 +133,7 @@ class FusedAdamClip:
         self._captures += 1
         self._tables[("prefetched", self._captures)] = self._pre                 # the graph owns these buffers
         self._pre = None
-        return [pinned, tdev, bdev, part, len(bmap), bpin]
+        return [pinned, tdev, bdev, part, len(bmap), bpin, None]
 
     def step(self) -> None:
         live = [p for p in self.params if p.grad is not None]
@@ -135,7 +144,6 @@ class FusedAdamClip:
                 self._pre = None
             return
         ent = self._table_prefetched(live) if pre is not None else self._table(live)
-        self.host_steps += 1
         L = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
         ops._count(2)

@@ -25,7 +25,7 @@ from .losses import pretrain_loss_syncfree, probe_loss
 
 class PretrainStep:
     def __init__(self, model, lr: float = 3e-3, max_grad_norm: Optional[float] = 5.0, loss: Union[str, Callable] = "probe",
-                 scaler_mean: float = 0.0, scaler_std: float = 1.0, use_graph: bool = True, reducer: Optional[_dp.FlatGradAllReduce] = None,
+                 scaler_mean: float = 0.0, scaler_std: float = 1.0, mask_value: float = 0.0, use_graph: bool = True, reducer: Optional[_dp.FlatGradAllReduce] = None,
                  optimizer: Optional[torch.optim.Optimizer] = None, fused_optimizer: bool = True):
         self.model = model
         self.enc = model.encoder
@@ -46,12 +46,12 @@ class PretrainStep:
                 self.loss_fn = lambda outs, src, ep: _ops.fused_probe_loss(outs, src, ep > self.enc.change_epoch)
             elif loss == "mask_mae":
                 self.loss_fn = lambda outs, src, ep: _ops.fused_mask_mae_loss(outs, src, ep > self.enc.change_epoch,
-                                                                              scaler_mean, scaler_std)
+                                                                              scaler_mean, scaler_std, mask_value)
             elif loss == "probe_torch":
                 self.loss_fn = lambda outs, src, ep: probe_loss(outs, src, ep, self.enc.change_epoch)
             elif loss == "mask_mae_torch":
                 self.loss_fn = lambda outs, src, ep: pretrain_loss_syncfree(outs, src, ep, self.enc.change_epoch, scaler_mean,
-                                                                            scaler_std, model.output_dim)
+                                                                            scaler_std, model.output_dim, mask_value)
             else:
                 raise ValueError(loss)
         else:
@@ -133,8 +133,11 @@ class PretrainStep:
                 torch.cuda.current_stream().wait_stream(side)
                 return loss
             self._capture(src, epoch, phase)
+            fresh = True                     # the capture drew this step's class order already (one shuffle per step, ref :357-358)
+        else:
+            fresh = False
         g, static_src, static_loss, plan_dev = self._graphs[key]
-        if plan_dev is not None:
+        if plan_dev is not None and not fresh:
             n = source.shape[0] * source.shape[1] * source.shape[2]
             plan_dev.copy_(self.enc.mask_plan(n, epoch), non_blocking=True)
         static_src.copy_(source, non_blocking=True)

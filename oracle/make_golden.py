@@ -13,6 +13,11 @@ oracle/ref_import.py; the reference ships no fixtures of its own)
   pems08_ckpt.npz      shipped PEMS08 checkpoint on the first 8 PEMS08 test windows: the input windows,
                        a strided sample + moments of the eval-mode encoder output, and the pretrain-mode
                        masked MAE / KL at epoch 1 and 300 (the SURVEY.md §8c numbers).
+  pems08_weights.npz   the shipped PEMS08 checkpoint itself (model/SAVE/PEMS08/GPTST_ada.pth, 159 tensors, a reference DATA artefact)
+                       as a plain npz, so that the checkpoint parity tests run on a box without /root/reference.
+  losses.npz           the trainer's loss (Run.py:91-101 `scaler_mae_loss` closure extracted with ast + lib/metrics.py MAE_torch +
+                       lib/normalization.py StandardScaler; KL of Run.py:132 / BasicTrainer.py:84-86) on seeded inputs, with
+                       values and gradients, for mask_value (args.mape_thresh) 0.0 and 0.001.
   eval_path.npz        eval-path pieces next to the encoder: the reference ``Fusion`` gate + ``lin_test``
                        and STGCN's ``TemporalConvLayer`` (GLU) in four channel / kernel configurations, with gradients.
 """
@@ -228,6 +233,61 @@ def pems08(ref, root):
     print("pems08_ckpt.npz", sum(v.size for v in out.values()), "elements")
 
 
+def pems08_weights():
+    ck = checkpoint_path("PEMS08")
+    if ck is None:
+        print("pems08_weights: checkpoint missing, skipped")
+        return
+    sd = torch.load(ck, map_location="cpu")
+    out = {"__order__": np.array(list(sd.keys()))}
+    out.update({k: npd(v) for k, v in sd.items()})
+    np.savez_compressed(os.path.join(GOLD, "pems08_weights.npz"), **out)
+    print("pems08_weights.npz", len(sd), "tensors", sum(v.numel() for v in sd.values()), "elements")
+
+
+def losses(root):
+    """Run.py's loss closure + KL on seeded (B,T,N,1) tensors (values in z-score space, as the trainer passes them)."""
+    import ast
+    import importlib.util
+
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+    metrics = load(os.path.join(root, "lib", "metrics.py"), "ref_metrics")
+    norm = load(os.path.join(root, "lib", "normalization.py"), "ref_norm")
+    src = open(os.path.join(root, "model", "Run.py")).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "scaler_mae_loss")
+    ns = {"MAE_torch": metrics.MAE_torch, "args": types.SimpleNamespace(mode="pretrain"), "torch": torch}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), "Run.py:scaler_mae_loss", "exec"), ns)
+    mean, std = 229.64618311390265, 145.64368009977818                       # PEMS08 scaler (SURVEY.md 8c)
+    scaler = norm.StandardScaler(mean, std)
+    torch.manual_seed(91)
+    B, T, N, H = 3, 12, 11, 5
+    pred = torch.randn(B, T, N, 1, requires_grad=True)
+    true = torch.randn(B, T, N, 1) * 1.2
+    true[0, :, 3] = -mean / std                                               # exact zeros after the inverse transform (sensor gaps)
+    true[1, :, 4] = (0.0005 - mean) / std                                     # 0 < value <= 0.001: kept by thresh 0, dropped by 0.001
+    inv_mask = (torch.rand(B, T, N, 1) < 0.25).long()
+    inv_mask[1, :, 4] = 1
+    inv_mask[0, 0:6, 3] = 1
+    prob = torch.softmax(torch.randn(B, T, N, H), -1).requires_grad_()
+    hs = torch.softmax(torch.randn(B, T, N, H), -1)
+    out = {"pred": npd(pred), "true": npd(true), "inv_mask": npd(inv_mask), "prob": npd(prob), "hs": npd(hs),
+           "scaler": np.array([mean, std])}
+    for tag, thr in (("thr0", 0.0), ("thr1e-3", 0.001)):
+        loss_fn = ns["scaler_mae_loss"](scaler, thr)
+        mae, _ = loss_fn(pred, true, inv_mask)                                # BasicTrainer.py:83
+        kl = torch.nn.KLDivLoss(reduction="sum")(prob.log(), hs) * 0.1        # BasicTrainer.py:85
+        tot = mae + kl
+        gp, gq = torch.autograd.grad(tot, [pred, prob])
+        out.update({f"{tag}.mae": np.array([mae.item()]), f"{tag}.kl": np.array([kl.item()]), f"{tag}.g.pred": npd(gp),
+                    f"{tag}.g.prob": npd(gq)})
+        print(f"losses {tag}: mae {mae.item():.6f} kl {kl.item():.6f}")
+    np.savez_compressed(os.path.join(GOLD, "losses.npz"), **out)
+
+
 def eval_path(root):
     """Fusion (model/Model.py:5-18, class source extracted with ast: the module itself imports the whole predictor zoo) and
     STGCN's TemporalConvLayer with GLU (model/STGCN/stgcn.py:25-53, imported as is) on seeded inputs, with all gradients."""
@@ -287,6 +347,8 @@ def main():
     model_case(ref, "pre_phase1_ibd2", small_cfg(input_base_dim=2), 2, 5, 50)
     model_case(ref, "pre_phase2_ibd2", small_cfg(input_base_dim=2), 2, 120, 60)
     pems08(ref, root)
+    pems08_weights()
+    losses(root)
     eval_path(root)
 
 

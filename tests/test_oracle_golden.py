@@ -139,14 +139,44 @@ def test_draws_replay_matches_torch_global_rng():
     assert o == d.class_order
 
 
+def load_pems08_weights():
+    w = np.load(os.path.join(GOLDEN, "pems08_weights.npz"))
+    return {str(k): torch.from_numpy(w[str(k)]) for k in w["__order__"]}
+
+
+def test_pems08_weights_fixture_is_the_shipped_checkpoint():
+    """tests/golden/pems08_weights.npz: 159 tensors in the reference's registration order; identical to the .pth when it is here."""
+    from oracle.ref_import import checkpoint_path
+    P = load_pems08_weights()
+    assert len(P) == 159 and sum(v.numel() for v in P.values()) == 1036579
+    ck = checkpoint_path("PEMS08")
+    if ck is not None:
+        sd = torch.load(ck, map_location="cpu")
+        assert list(sd.keys()) == list(P.keys())
+        assert all(torch.equal(sd[k], P[k]) for k in sd)
+
+
+@pytest.mark.parametrize("tag,thr", [("thr0", 0.0), ("thr1e-3", 0.001)])
+def test_loss_oracle_matches_reference_trainer_loss(tag, thr):
+    """O.masked_mae / O.kl_sum against the reference's own loss closure (Run.py:91-101 -> lib/metrics.py:11-18, KL of
+    BasicTrainer.py:84-86) on the fixture generated by oracle/make_golden.py `losses`."""
+    g = np.load(os.path.join(GOLDEN, "losses.npz"))
+    pred, prob = T(g["pred"]).requires_grad_(), T(g["prob"]).requires_grad_()
+    true, inv, hs = T(g["true"]), torch.from_numpy(g["inv_mask"]), T(g["hs"])
+    mean, std = (float(v) for v in g["scaler"])
+    mae = O.masked_mae(pred, true, inv, mean, std, thr)
+    kl = 0.1 * O.kl_sum(prob, hs)
+    assert abs(mae.item() - float(g[f"{tag}.mae"][0])) <= 1e-5 * float(g[f"{tag}.mae"][0])
+    assert abs(kl.item() - float(g[f"{tag}.kl"][0])) <= 1e-5 * float(g[f"{tag}.kl"][0])
+    gp, gq = torch.autograd.grad(mae + kl, [pred, prob])
+    close(gp, T(g[f"{tag}.g.pred"]), atol=1e-7, rtol=1e-5, what="d loss / d pred")
+    close(gq, T(g[f"{tag}.g.prob"]), atol=1e-7, rtol=1e-5, what="d loss / d prob")
+
+
 def test_pems08_checkpoint_golden():
     """Shipped PEMS08 checkpoint, first 8 test windows (SURVEY.md §8c numbers)."""
-    from oracle.ref_import import checkpoint_path
-    ck = checkpoint_path("PEMS08")
-    if ck is None:
-        pytest.skip("reference checkpoint not available (no /root/reference, no baseline/_ref)")
     g = np.load(os.path.join(GOLDEN, "pems08_ckpt.npz"))
-    P = torch.load(ck, map_location="cpu")
+    P = load_pems08_weights()                      # the shipped checkpoint as a committed fixture: runs without /root/reference
     x = T(g["x"])
     assert abs(float(x[0, 0, 0, 0]) - 1.3344) < 1e-4
 
