@@ -33,11 +33,23 @@ import torch  # noqa: E402
 
 T_STEPS = 12
 WORKLOADS = {
-    # name: (N, D, per-GPU batch)
-    "pems08": (170, 64, 64),
-    "metr_la": (207, 64, 64),
-    "synthetic2048": (2048, 128, 16),
+    # name: (N, D, per-GPU batch at one GPU)
+    "pems08": (170, 64, 64),          # BASELINE.json configs[1]; weak scaling (64 per GPU)
+    "metr_la": (207, 64, 64),         # configs[2]; weak scaling
+    "synthetic2048": (2048, 128, 128),  # configs[3]; STRONG scaling: global batch 128 split over the ranks
 }
+STRONG = {"synthetic2048"}
+
+
+def per_gpu_batch(name, world, override=0):
+    B = WORKLOADS[name][2]
+    if override:
+        return override
+    if name in STRONG:
+        if B % world:
+            raise SystemExit(f"{name}: global batch {B} is not divisible by {world} ranks")
+        return B // world
+    return B
 
 
 def make_cfg(N, D, device):
@@ -170,31 +182,42 @@ def time_cpu(step, steps, warmup, budget_s=None):
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the step on the host cores, on OUR arm's config: same workload dict, same
+    GLOBAL batch as our arm runs at this --gpus (weak scaling: 64 x N; strong: 128).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    N, D, B = WORKLOADS[args.workload]
+    N, D, _ = WORKLOADS[args.workload]
+    world = max(1, args.gpus)
+    Bg = per_gpu_batch(args.workload, world, args.batch)
+    B = Bg * world                                    # the CPU runs the whole global batch of one step
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     step, kind = cpu_reference_stepper(N, D, B, args.epoch)
-    sec, done = time_cpu(step, args.steps, args.warmup)
+    sec, done = time_cpu(step, args.steps, args.warmup, budget_s=150.0)
     value = B / sec
     line = {
         "impl": "reference", "metric": "pretrain samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload in STRONG else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, B, 1, args.epoch) | {"device": "host CPU"},
+        "config": workload_config(args.workload, Bg, world, args.epoch),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind,
-                         "sample": f"{done} full training steps at batch {B} after {args.warmup} warm-up, all {cores} host threads"},
+                         "sample": f"{done} full training steps at global batch {B} after {args.warmup} warm-up, all {cores} host threads"},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
 
 
+L2_NOTE = ("no flush between steps: one step touches ~2 GB of activations/gradients >> 126 MB L2; "
+           "kernel roofline timed on rotating buffer sets > L2")
+
+
 def workload_config(name, B, world, epoch):
+    """The SAME dict on both arms (ours / --impl reference): the driver compares them key by key."""
     N, D, _ = WORKLOADS[name]
-    return {"workload": f"{name}: GPT-ST pretrain step, N={N}, T=12, D={D}, batch {B}/GPU (BASELINE.json configs[1] geometry)"
+    return {"l2": L2_NOTE, "workload": f"{name}: GPT-ST pretrain step, N={N}, T=12, D={D}, batch {B}/GPU (BASELINE.json configs[1] geometry)"
             if name == "pems08" else f"{name}: GPT-ST pretrain step, N={N}, T=12, D={D}, batch {B}/GPU",
             "global_batch": B * world, "per_gpu_batch": B, "num_nodes": N, "hidden_dim": D, "epoch_arg": epoch,
             "mask_phase": "adaptive+KL" if epoch > 10 else "random", "optimizer": "Adam lr 3e-3, clip_grad_norm 5",
@@ -271,39 +294,67 @@ def hypertem_forward_time(N, D, B, iters=20):
 
 
 def kernel_rooflines(N, D, B, peak, iters=20):
-    """The two kernels that dominate the step (gptst_gproj_bwd time-grouped = hyperTem's projection backward, 8 launches, and
-    gptst_tmix_bwd, 8 launches) timed alone with CUDA events on rotating buffer sets > L2, against their algorithmic bytes."""
-    from gptst_b200 import ops
+    """Other kernels of the step timed alone (CUDA events, graph replays, rotating buffer sets > L2) against their algorithmic
+    bytes: the fused hyperTem backward on the main chain (reads dOut, writes deb + dret: 3A; SURVEY.md 8d counts 12*B*T*N*D = 3A
+    for the whole hyperTem backward), its two side-stream parameter-gradient kernels, and cap's node-grouped projection backward."""
+    from gptst_b200 import _lib, ops
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(2)
     A = 4 * B * T_STEPS * N * D
     nset = max(3, int(400e6 // (5 * A)) + 1)
     sets = [[torch.randn(B, T_STEPS, N, D, device=dev, generator=g) for _ in range(4)] for _ in range(nset)]
-    W = torch.randn(B, 12, D, D, device=dev, generator=g) * D ** -0.5
-    Mn = torch.randn(N, 12, 12, device=dev, generator=g) * 0.2
     prec = ops.default_precision()
     out = {}
 
     def timeit(fn):
         return time_graph_replays([(lambda st=st: fn(st)) for st in sets], iters)
 
+    def entry(ms, algo, launches):
+        return {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9, "frac": algo / (ms * 1e-3) / 1e9 / peak,
+                "unit": "GB/s", "launches_per_step": launches}
+
     with torch.no_grad():
-        # the call also sums its (splits == 1) partials: a view, no extra kernel
-        ms = timeit(lambda s: ops.gproj_bwd(s[0], s[1], s[2], W, node_grouped=False, act=True, prec=prec, want_dres=True))
-        algo = 5 * A + 2 * 4 * B * 12 * D * D     # dY, Y, X in; dX, dRes out; W_bt in, dW_bt out
-        out["gproj_bwd_time_grouped"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
-                                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
-        if D == 64:                               # the fused mix backward exists for D = 64 (D = 128 uses tmix + tmix_dM)
-            ms = timeit(lambda s: ops.tmix_bwd(s[0], s[1], Mn, s[2], prec))
-            algo = 4 * A                          # dy, x in; dx read-modify-write
-            out["tmix_bwd"] = {"ms": ms, "algorithmic_bytes": algo, "achieved": algo / (ms * 1e-3) / 1e9,
-                               "frac": algo / (ms * 1e-3) / 1e9 / peak, "unit": "GB/s", "launches_per_step": 8}
+        if ops.hypertem_fused_enabled(D, T_STEPS, prec):
+            L = _lib.lib()
+            W = torch.randn(B, 12, D, D, device=dev, generator=g) * D ** -0.5
+            Mn = torch.randn(N, 12, 12, device=dev, generator=g) * 0.2
+            nb = L.gptst_hypertem_wfrag_bytes(B * 12)
+            wf, wb = (torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(2))
+            st0 = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.gptst_hypertem_pack_w(W.data_ptr(), wf.data_ptr(), wb.data_ptr(), B * 12, st0), "pack")
+            npad = (N + 15) // 16 * 16
+            mask = torch.randint(-2 ** 31, 2 ** 31 - 1, (B * 12, npad, 2), device=dev, dtype=torch.int32)
+            sp_w, sp_m = L.gptst_gproj_splits(B * 12, N, D), L.gptst_tmix_bwd_splits(B, N)
+            dWp = torch.empty((sp_w, B * 12, D, D), device=dev)
+            dbp = torch.empty((sp_w, B * 12, D), device=dev)
+            dMp = torch.empty((sp_m, N, 12, 12), device=dev)
+            cs = lambda: torch.cuda.current_stream().cuda_stream
+            ms = timeit(lambda s: _lib.check(L.gptst_hypertem_bwd(s[0].data_ptr(), mask.data_ptr(), Mn.data_ptr(), wb.data_ptr(), s[1].data_ptr(),
+                                                                  s[2].data_ptr(), B, 12, N, D, cs()), "bwd"))
+            out["hypertem_bwd_fused"] = entry(ms, 3 * A, 8)
+            ms = timeit(lambda s: _lib.check(L.gptst_hypertem_dw(s[0].data_ptr(), mask.data_ptr(), s[3].data_ptr(), dWp.data_ptr(), dbp.data_ptr(),
+                                                                 B, 12, N, D, npad, sp_w, cs()), "dw"))
+            out["hypertem_dw_side_stream"] = entry(ms, 2 * A + 4 * B * 12 * D * D, 8)
+            ms = timeit(lambda s: _lib.check(L.gptst_tmix_dM2(s[2].data_ptr(), s[3].data_ptr(), dMp.data_ptr(), B, 12, N, D, sp_m, cs()), "dM"))
+            out["hypertem_dM_side_stream"] = entry(ms, 2 * A, 8)
+        Wn = torch.randn(N, D, D, device=dev, generator=g) * D ** -0.5
+        ms = timeit(lambda s: ops.gproj_bwd(s[0], s[1], s[2], Wn, node_grouped=True, act=True, prec=prec, want_dres=True, sum_parts=False))
+        out["gproj_bwd_node_grouped"] = entry(ms, 5 * A, 4)
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one cap forward, from the committed
-# `ncu --set full` capture (profiles/ncu_cap_forward_r01_b.md); only known for the geometry that was captured.
-NCU_TRAFFIC_BYTES = {("pems08", 64): 125.5e6}
+def ncu_traffic(workload, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels of ONE cap forward, per launch of the chain, from the
+    committed `ncu --set full` summary of `python bench.py --cap-only` (tools/ncu_cap_traffic.sh writes
+    profiles/ncu_cap_forward_traffic.json with the kernel list, the geometry and the commit it was taken at).  None when no
+    capture exists for this geometry: bench.py cannot run ncu on itself, so this is a committed measurement, not a live one."""
+    try:
+        d = json.load(open(os.path.join(REPO, "profiles", "ncu_cap_forward_traffic.json")))
+        if d.get("workload") == workload and int(d.get("batch", -1)) == B:
+            return float(d["dram_bytes_per_chain"]), d.get("source")
+    except Exception:
+        pass
+    return None, None
 
 
 def measured_peak():
@@ -327,10 +378,13 @@ def run_ours(args):
         args.gpus = world
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    N, D, B = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
+    N, D, _ = WORKLOADS[args.workload]
+    B = per_gpu_batch(args.workload, world, args.batch)
     epoch = args.epoch
+    if args.cap_only:              # the roofline leg alone (what tools/ncu_cap_traffic.sh profiles); never a bench line
+        algo, cap_ms = cap_forward_roofline(N, D, B, iters=6)
+        print(json.dumps({"cap_only": True, "workload": args.workload, "batch": B, "algorithmic_bytes": algo, "ms": cap_ms}), flush=True)
+        return 0
     cfg = make_cfg(N, D, "cuda")
     model = GPTST_Model(cfg).to(dev)
     run_init(model, 0)
@@ -406,19 +460,18 @@ def run_ours(args):
         step_bytes = (60 * 4 * B * T_STEPS * N * D) + (8 * 4 * B * T_STEPS * N * 10)
         line = {
             "metric": "pretrain samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core contractions, fp32 accumulate)"
-            if ops.default_precision() == 3 else "tf32 operands, fp32 accumulate",
-            "data": "synthetic", "config": workload_config(args.workload, B, world, epoch) | {
-                "l2": "no flush between steps: one step touches ~2 GB of activations/gradients >> 126 MB L2; "
-                      "kernel roofline timed on rotating buffer sets > L2"},
+            "warmup": max(4, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak",
+            "vs_baseline": None, "dtype": "f32 (tensor-core contractions as three-term fp16 splits, fp32 accumulate; fp32 FMA elsewhere)"
+            if ops.default_precision() == 3 else "f32 storage, single-term fp16/tf32 tensor-core operands, fp32 accumulate",
+            "data": "synthetic", "config": workload_config(args.workload, B, world, epoch),
             "e2e": {"value": value_e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "step_mode": "eager" if args.eager else "one CUDA graph per step (gptst_b200.train.PretrainStep)",
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "cap forward (gptst_cap_route_fwd + gptst_cap_hop_e1 + gptst_cap_recon_hop + "
                          "gptst_gproj_fwd), the hypergraph + node-adaptive GCN block named by BASELINE.json", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get((args.workload, B)), "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload, B)[0], "traffic_source": ncu_traffic(args.workload, B)[1],
+                         "algorithmic_bytes": algo, "ms": cap_ms, "peak_source": peak_src},
             "roofline_hypertem_fwd": {"achieved": ht_algo / (ht_ms * 1e-3) / 1e9, "unit": "GB/s", "ms": ht_ms,
                                       "algorithmic_bytes": ht_algo, "frac": ht_algo / (ht_ms * 1e-3) / 1e9 / peak},
             "roofline_kernels": kernel_rooflines(N, D, B, peak),
@@ -460,6 +513,7 @@ def main():
                     help="bracket the timed (resident-input) steps with cudaProfilerStart/Stop: `ncu --profile-from-start off "
                          "--metrics gpu__time_duration.sum ... python bench.py --steps 2 --warmup 1 --profiler-range --no-rooflines "
                          "--no-cpu-baseline` lists exactly the kernels of the timed graph replays (never a bench value)")
+    ap.add_argument("--cap-only", action="store_true", help="run only the cap-forward roofline leg (for ncu captures; not a bench line)")
     ap.add_argument("--no-rooflines", action="store_true", help="A/B runs: print only the step numbers (not a bench line)")
     ap.add_argument("--eager", action="store_true", help="time the eager step (what an unmodified Run.py loop launches) instead of the graph")
     args = ap.parse_args()

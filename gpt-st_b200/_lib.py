@@ -28,7 +28,6 @@ SIGNATURES = {
     "gptst_cap_recon": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_e1": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon_hop": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
-    "gptst_cap_recon_hop3": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_recon_hop_fused": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_dv_dcr": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_hop_bwd": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
@@ -64,9 +63,7 @@ SIGNATURES = {
     "gptst_affine1_fwd": (_i, [_f, _f, _f, _f, _l, _i, _f]),
     "gptst_affine1_bwd_parts": (_i, [_l]),
     "gptst_affine1_bwd": (_i, [_f, _f, _f, _l, _i, _i, _f]),
-    "gptst_gproj3_fwd": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _f]),
     "gptst_gproj3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _i, _i, _f]),
-    "gptst_tmix3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_hypertem_wfrag_bytes": (_l, [_i]),
     "gptst_hypertem_mask_pad_rows": (_i, []),
     "gptst_hypertem_pack_w": (_i, [_f, _f, _f, _i, _f]),

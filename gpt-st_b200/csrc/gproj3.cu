@@ -1,15 +1,11 @@
-// EXPERIMENTAL third generation of the grouped D x D projection (D = 64), NOT on the default path: reachable only through
-// gptst_gproj3_fwd / gptst_gproj3_bwd (checked against gproj2 by tools/gproj3_check.cu; not wired into ops.py yet).  Same decomposition as gproj2.cu (one warp per
-// 16-row tile, three-term fp16 split, cp.async staged rows); two changes that profiles/ncu_gproj2_bwd_r01.md asks for:
-//   * the forward kernel also writes a packed SIGN MASK of its output (one bit per element, 8 bytes per row) and the
-//     backward reads that mask instead of Y: LeakyReLU's derivative needs nothing else.  The backward's traffic drops from
-//     5A to 4A and the exposed global latency of the Y rows (31 % of the stall samples of the time-grouped launch) is gone;
-//   * ONE power-of-two scale per WARP tile instead of per CTA chunk: dX is a per-warp product anyway, and for dW the
-//     un-scaling moves into the row-tile loop (dW += dW_tile * (sx_tile * sg_tile)), which removes both block-wide max
-//     exchanges and their barriers (17 % of the stall samples).
-//   * (added after the check of profiles/gproj3_check_r01.log, not yet timed) with dX accumulated in place the old dX rows
-//     are prefetched into L2 together with the staging copies: their read in the epilogue was 27 % of the stall samples.
-// Everything else (staging, operand layouts, dW ownership, determinism) is unchanged, see gproj2.cu.
+// Sign-mask backward of the grouped D x D projection (D = 64): same decomposition as gproj2.cu (one warp per 16-row tile,
+// three-term fp16 split, cp.async staged rows) with two differences that profiles/ncu_gproj2_bwd_r01.md asked for:
+//   * LeakyReLU's derivative comes from a packed SIGN MASK of the forward output (8 bytes per row) instead of re-reading Y:
+//     traffic 5A -> 4A and no exposed global latency on the Y rows;
+//   * ONE power-of-two scale per WARP tile instead of per CTA chunk (no block-wide max exchange): for dW the un-scaling moves
+//     into the row-tile loop (dW += dW_tile * (sx_tile * sg_tile)).
+// Default use (round 2): flags 4|8 = the dW_bt / db_bt kernel of the fused hyperTem backward (gptst_hypertem_dw), fed by the
+// mask the fused forward writes.  The general entry point gptst_gproj3_bwd is kept for the stand-alone checks.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -47,111 +43,6 @@ __device__ __forceinline__ void prefetch_rows16(const float* base, long rs, int 
 
 __device__ __forceinline__ int kperm(int j) {   // physical k (mod 16) -> logical MMA k of the ldmatrix-from-fp32 A operand
     return (j < 4) ? 2 * j : (j < 8) ? 2 * (j - 4) + 1 : (j < 12) ? 8 + 2 * (j - 8) : 8 + 2 * (j - 12) + 1;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------------------------
-template <int NW, int MINB, int PREC>
-__global__ void __launch_bounds__(NW * 32, MINB)
-gproj3_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* __restrict__ Res, float* __restrict__ Y, uint2* __restrict__ Mask, int R, long gs, long rs, int act,
-                  int chunks) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    unsigned char* Xs = smraw;                                   // [NW*16][ROWB]
-    unsigned char* Wt = Xs + (size_t)NW * 16 * ROWB;             // [64][ROWB]  W_g planes, row = logical k
-    float* bs = reinterpret_cast<float*>(Wt + (size_t)D * ROWB); // [64]
-    unsigned char* Rs = reinterpret_cast<unsigned char*>(bs + D);// [NW*16][ROWB] (only when Res != nullptr)
-
-    constexpr int NT = NW * 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int grp = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
-    const int n0 = warp * 16;
-    const int r0 = chunk * NW * 16 + n0;
-    const float* Xg = X + (long)grp * gs;
-    stage16(Xs + (size_t)n0 * ROWB, Xg, rs, r0, R, lane);
-    if (Res) stage16(Rs + (size_t)n0 * ROWB, Res + (long)grp * gs, rs, r0, R, lane);
-    const float* Wg = W + (size_t)grp * D * D;
-    {   // all of this thread's W_g loads are issued before the first one is consumed (a rolled loop serialises the latencies)
-        constexpr int WI = (D * 16 + NT - 1) / NT;
-        float4 wv[WI];
-#pragma unroll
-        for (int u = 0; u < WI; ++u) {
-            const int i = tid + u * NT;
-            wv[u] = (i < D * 16) ? *reinterpret_cast<const float4*>(Wg + (size_t)(i >> 4) * D + (i & 15) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < WI; ++u) {
-            const int i = tid + u * NT;
-            if (i < D * 16) {
-                const int k = i >> 4, q4 = i & 15;
-                uint32_t h0, l0, h1, l1;
-                split_h2<PREC>(wv[u].x * WSCALE, wv[u].y * WSCALE, h0, l0);
-                split_h2<PREC>(wv[u].z * WSCALE, wv[u].w * WSCALE, h1, l1);
-                unsigned char* row = Wt + (size_t)(16 * (k >> 4) + kperm(k & 15)) * ROWB + q4 * 8;
-                *reinterpret_cast<uint2*>(row) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(row + LO) = make_uint2(l0, l1);
-            }
-        }
-    }
-    for (int i = tid; i < D; i += NT) bs[i] = bias ? bias[(size_t)grp * D + i] : 0.f;
-    cp_async_wait_all();
-    __syncthreads();
-    if (r0 >= R) return;   // whole tile out of range (no further block-wide barrier below)
-
-    float acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        uint32_t f[4], ah[4], al[4];
-        const uint32_t aaddr = smem_u32(Xs + (size_t)(n0 + (lane & 7)) * ROWB + (16 * b + 4 * (lane >> 3)) * 4);
-        ldsm_x4(f, aaddr);
-        split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[0], al[0]);
-        split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[2], al[2]);
-        ldsm_x4(f, aaddr + 8 * ROWB);
-        split_h2<PREC>(__uint_as_float(f[0]), __uint_as_float(f[1]), ah[1], al[1]);
-        split_h2<PREC>(__uint_as_float(f[2]), __uint_as_float(f[3]), ah[3], al[3]);
-#pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
-            uint32_t bh[4], bl[4] = {0u, 0u, 0u, 0u};
-            const uint32_t baddr =
-                smem_u32(Wt + (size_t)(16 * b + 8 * ((lane >> 3) & 1) + (lane & 7)) * ROWB + (16 * jp + 8 * (lane >> 4)) * 2);
-            ldsm_x4_t(bh, baddr);
-            if (PREC == PREC_3XTF32) ldsm_x4_t(bl, baddr + LO);
-            mma3<PREC>(acc[2 * jp], ah, al, bh[0], bh[1], bl[0], bl[1]);
-            mma3<PREC>(acc[2 * jp + 1], ah, al, bh[2], bh[3], bl[2], bl[3]);
-        }
-    }
-    constexpr float inv = 1.f / WSCALE;
-    float* Yg = Y + (long)grp * gs;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int rl = n0 + g + 8 * half, rg = r0 + g + 8 * half;
-        uint32_t mlo = 0u, mhi = 0u;       // sign bits of this lane's 16 outputs of the row: bit c = (y[c] > 0)
-        if (rg < R) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int col = 8 * j + 2 * t;
-                float y0 = fmaf(acc[j][2 * half], inv, bs[col]), y1 = fmaf(acc[j][2 * half + 1], inv, bs[col + 1]);
-                if (Res) {
-                    const float2 rr = *reinterpret_cast<const float2*>(Rs + (size_t)rl * ROWB + col * 4);
-                    y0 += rr.x; y1 += rr.y;
-                }
-                if (act) { y0 = lrelu(y0); y1 = lrelu(y1); }
-                *reinterpret_cast<float2*>(Yg + (long)rg * rs + col) = make_float2(y0, y1);
-                const uint32_t two = (y0 > 0.f ? 1u : 0u) | (y1 > 0.f ? 2u : 0u);
-                if (j < 4) mlo |= two << (8 * j + 2 * t);
-                else mhi |= two << (8 * (j - 4) + 2 * t);
-            }
-        }
-        if (Mask) {                        // uniform over the grid; the four lanes of a quad hold the row's 64 bits between them
-            mlo |= __shfl_xor_sync(0xffffffffu, mlo, 1); mlo |= __shfl_xor_sync(0xffffffffu, mlo, 2);
-            mhi |= __shfl_xor_sync(0xffffffffu, mhi, 1); mhi |= __shfl_xor_sync(0xffffffffu, mhi, 2);
-            if (t == 0 && rg < R) Mask[((long)grp * gs + (long)rg * rs) / D] = make_uint2(mlo, mhi);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -453,18 +344,6 @@ static int pick_nw(int R) {   // warps (= 16-row tiles) per CTA chunk
 }
 
 template <int NW, int MINB, int PREC>
-static cudaError_t launch_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, uint2* Mask, int G,
-                              int R, long gs, long rs, int act, cudaStream_t st) {
-    const int chunks = (R + NW * 16 - 1) / (NW * 16);
-    const size_t smem = (size_t)NW * 16 * ROWB * (Res ? 2 : 1) + (size_t)D * ROWB + D * 4;
-    auto kern = gproj3_fwd_kernel<NW, MINB, PREC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((size_t)G * chunks), NW * 32, smem, st>>>(X, W, bias, Res, Y, Mask, R, gs, rs, act, chunks);
-    return cudaGetLastError();
-}
-
-template <int NW, int MINB, int PREC>
 static cudaError_t launch_bwd(const float* dY, const uint2* Mask, const float* X, const float* W, float* dX, float* dWp,
                               float* dbp, float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, int mrs, cudaStream_t st) {
     const int chunks = (R + NW * 16 - 1) / (NW * 16);
@@ -488,11 +367,6 @@ static cudaError_t launch_bwd(const float* dY, const uint2* Mask, const float* X
     }
 
 template <int PREC>
-static cudaError_t fwd_p(const float* X, const float* W, const float* bias, const float* Res, float* Y, uint2* Mask, int G, int R,
-                         long gs, long rs, int act, cudaStream_t st) {
-    GP2_DISPATCH(launch_fwd, X, W, bias, Res, Y, Mask, G, R, gs, rs, act, st)
-}
-template <int PREC>
 static cudaError_t bwd_p(const float* dY, const uint2* Mask, const float* X, const float* W, float* dX, float* dWp, float* dbp,
                          float* dRes, int G, int R, long gs, long rs, int act, int splits, int flags, int mrs, cudaStream_t st) {
     GP2_DISPATCH(launch_bwd, dY, Mask, X, W, dX, dWp, dbp, dRes, G, R, gs, rs, act, splits, flags, mrs, st)
@@ -505,18 +379,6 @@ int gproj2_splits(int G, int R);     // gproj2.cu: the split policy is shared (s
 }  // namespace gptst
 
 using namespace gptst;
-
-// EXPERIMENTAL (see the header comment).  mask: (rows, 2) uint32 = 64 sign bits per row of Y, rows in Y's memory order (row =
-// element offset / D); may be NULL in the forward (then identical to gptst_gproj_fwd for D = 64).  splits = gptst_gproj_splits.
-extern "C" int gptst_gproj3_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, void* mask, int G,
-                                int R, long group_stride, long row_stride, int D, int act, int prec, void* stream) {
-    if (!X || !W || !Y || G <= 0 || R <= 0) return -1;
-    if (D != 64 || (prec != 1 && prec != 3) || group_stride % D != 0 || row_stride % D != 0) return -2;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (prec == PREC_3XTF32)
-        return (int)gp3::fwd_p<PREC_3XTF32>(X, W, bias, Res, Y, (uint2*)mask, G, R, group_stride, row_stride, act, st);
-    return (int)gp3::fwd_p<PREC_TF32>(X, W, bias, Res, Y, (uint2*)mask, G, R, group_stride, row_stride, act, st);
-}
 
 // flags: bit 0 = dX accumulated in place, bit 1 = W / dW are [out][in] (as gptst_linear_bwd_acc); mask is required when act != 0
 extern "C" int gptst_gproj3_bwd(const float* dY, const void* mask, const float* X, const float* W, float* dX, float* dW_part,

@@ -127,59 +127,6 @@ def gproj_bwd(dY, Y, X, W, *, node_grouped: bool, act: bool, prec: int, want_dre
     return dX, dW, db, dres
 
 
-def gproj3_enabled(D: int) -> bool:
-    """EXPERIMENTAL sign-mask projection kernels (csrc/gproj3.cu) for the time-grouped projection of hyperTem: opt-in with
-    GPTST_B200_GPROJ3=1.  Kernel-level check on the B200 (tools/gproj3_check.cu, profiles/gproj3_check_r01.log): outputs
-    bit-identical to the default kernels (dW to 8e-7), backward 69 -> 59 us, forward +1.7 us for writing the mask."""
-    return D == 64 and os.environ.get("GPTST_B200_GPROJ3", "0") == "1"
-
-
-def gproj3_fwd(X, W, bias, res, *, act: bool, prec: int):
-    """Time-grouped Y = act(X W_bt + b_bt + res) that also returns the packed sign mask of Y ((B*T*N, 2) int32)."""
-    B, T, N, D = X.shape
-    X, W, bias, res = _c(X), _c(W), _c(bias), _c(res)
-    _chk(X, W)
-    Y = torch.empty_like(X)
-    mask = torch.empty((B * T * N, 2), device=X.device, dtype=torch.int32)
-    rc = _lib.lib().gptst_gproj3_fwd(_p(X), _p(W), _p(bias), _p(res), _p(Y), _p(mask), B * T, N, N * D, D, D, int(act), prec, _stream())
-    _lib.check(rc, "gptst_gproj3_fwd")
-    return Y, mask
-
-
-def gproj3_bwd(dY, mask, X, W, *, act: bool, prec: int, want_dres: bool):
-    """Backward of `gproj3_fwd` from the sign mask (Y is not read): (dX, dW (B*T, D, D), db (B*T, D), dRes)."""
-    B, T, N, D = X.shape
-    dY, X, W = _c(dY), _c(X), _c(W)
-    _chk(dY, X, W)
-    L = _lib.lib()
-    G, R = B * T, N
-    splits = L.gptst_gproj_splits(G, R, D)
-    dX = torch.empty_like(X)
-    dWp = torch.empty((splits, G, D, D), device=X.device, dtype=torch.float32)
-    dbp = torch.empty((splits, G, D), device=X.device, dtype=torch.float32)
-    dres = torch.empty_like(X) if want_dres else None
-    rc = L.gptst_gproj3_bwd(_p(dY), _p(mask) if act else None, _p(X), _p(W), _p(dX), _p(dWp), _p(dbp), _p(dres), G, R, N * D, D, D,
-                            int(act), prec, splits, 0, _stream())
-    _lib.check(rc, "gptst_gproj3_bwd")
-    dW, db = sum_partials(dWp, dbp)
-    return dX, dW, db, dres
-
-
-def tmix3_bwd(dy, x, M, dout, mask, prec):
-    """EXPERIMENTAL (csrc/tmix3.cu): (dx, dM partials) with dx = dout * act'(mask) + M^T o dy written in one pass -- the companion of
-    `gproj3_bwd(..., want_dres=False)`; kernel-level check in tools/gproj3_check.cu."""
-    B, T, N, D = x.shape
-    dy, x, M, dout = _c(dy), _c(x), _c(M), _c(dout)
-    _chk(dy, x, M, dout)
-    L = _lib.lib()
-    splits = L.gptst_tmix_bwd_splits(B, N)
-    dx = torch.empty_like(x)
-    part = torch.empty((splits, N, T, T), device=x.device, dtype=torch.float32)
-    rc = L.gptst_tmix3_bwd(_p(dy), _p(x), _p(M), _p(dout), _p(mask), _p(dx), _p(part), B, T, N, D, prec, splits, _stream())
-    _lib.check(rc, "gptst_tmix3_bwd")
-    return dx, part
-
-
 def tmix(x, M, out=None, *, transpose=False, accumulate=False):
     B, T, N, D = x.shape
     x, M = _c(x), _c(M)
@@ -290,30 +237,16 @@ class _HyperTemCore(torch.autograd.Function):
             raise RuntimeError("hypertem_core: Mn must be expanded to (hypertem_partial_count(B, N, D), N, T, T)")
         Mn = Mn_e[0].contiguous()
         ret = tmix(eb, Mn)
-        ctx.use3 = gproj3_enabled(D)
-        if ctx.use3:       # experimental: the backward reads a packed sign mask instead of `out`
-            out, mask = gproj3_fwd(ret, W, bias, eb, act=True, prec=prec)
-            ctx.save_for_backward(eb, Mn, W, ret, mask)
-        else:
-            out = gproj_fwd(ret, W, bias, eb, node_grouped=False, act=True, prec=prec)
-            ctx.save_for_backward(eb, Mn, W, ret, out)
+        out = gproj_fwd(ret, W, bias, eb, node_grouped=False, act=True, prec=prec)
+        ctx.save_for_backward(eb, Mn, W, ret, out)
         ctx.prec = prec
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        eb, Mn, W, ret, out = ctx.saved_tensors           # `out` is the sign mask on the experimental path
+        eb, Mn, W, ret, out = ctx.saved_tensors
         dout = dout.contiguous()
-        if ctx.use3 and os.environ.get("GPTST_B200_TMIX3", "0") == "1":
-            # experimental pair: no dRes store in the projection backward, the mix backward rebuilds it from dout and the mask
-            B, T, N, D = eb.shape
-            dret, dW, db, _ = gproj3_bwd(dout, out, ret, W, act=True, prec=ctx.prec, want_dres=False)
-            deb, dM_part = tmix3_bwd(dret, eb, Mn, dout, out, ctx.prec)
-            return deb, dM_part, dW.view(B, T, D, D), db.view(B, T, D), None
-        if ctx.use3:
-            dret, dW, db, deb = gproj3_bwd(dout, out, ret, W, act=True, prec=ctx.prec, want_dres=True)
-        else:
-            dret, dW, db, deb = gproj_bwd(dout, out, ret, W, node_grouped=False, act=True, prec=ctx.prec, want_dres=True)
+        dret, dW, db, deb = gproj_bwd(dout, out, ret, W, node_grouped=False, act=True, prec=ctx.prec, want_dres=True)
         B, T, N, D = eb.shape
         if D == 64:
             dM_part = tmix_bwd(dret, eb, Mn, deb, ctx.prec, raw=True)

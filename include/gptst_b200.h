@@ -98,10 +98,6 @@ int gptst_cap_recon_hop(const float* c, const float* s, const float* dyn, const 
  * the backward pass.  Opt-in (GPTST_B200_HOP=fused): measured slower than the split pair on the B200 (80 us vs 6.5 + 22 us).   */
 int gptst_cap_recon_hop_fused(const float* c, const float* s, const float* dyn, float* e1, float* v, float* recon, int B, int T,
                               int N, int D, int H, int HT, void* stream);
-/* EXPERIMENTAL variant of gptst_cap_recon_hop (csrc/cap_hop3.cu; not used by the Python side yet): the thread's column quad of every
- * v row is kept in registers across the nodes it reconstructs (5x fewer shared-memory reads); bit-identical results expected.    */
-int gptst_cap_recon_hop3(const float* c, const float* s, const float* dyn, const float* e1, float* v, float* recon, int B, int T,
-                         int N, int D, int H, int HT, void* stream);
 /* ---- cap backward pieces ------------------------------------------------------
  * dv = c drecon, dcr = v drecon^T                                                                            */
 int gptst_cap_dv_dcr(const float* c, const float* v, const float* drecon, float* dv, float* dcr, int B, int T, int N,
@@ -203,21 +199,12 @@ int gptst_sum_partials(const float* const* ins, float* const* outs, const long* 
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
-/* EXPERIMENTAL third generation of gptst_gproj_fwd / _bwd for D = 64 (csrc/gproj3.cu; not used by the Python side yet): the forward
- * also writes a packed sign mask of Y (mask: (rows, 2) uint32, 64 bits per row of Y in Y's memory order, bit c = Y[row][c] > 0;
- * may be NULL) and the backward reads that mask instead of Y (LeakyReLU's derivative needs nothing else: 4A instead of 5A of
- * traffic) and scales its fp16 operands per warp tile instead of per CTA chunk (no block-wide max exchanges).  flags as in
- * gptst_linear_bwd_acc: bit 0 = dX accumulated in place, bit 1 = W / dW are [out][in].  splits = gptst_gproj_splits(G, R, D).   */
-int gptst_gproj3_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, void* mask, int G, int R,
-                     long group_stride, long row_stride, int D, int act, int prec, void* stream);
+/* Sign-mask backward of gptst_gproj_fwd for D = 64 (csrc/gproj3.cu): dy = dY * act'(mask) with mask = 8 bytes per row of Y
+ * (bit c = Y[c] > 0, rows in Y's memory order).  flags: bit 0 = dX accumulated in place, bit 1 = W / dW are [out][in].
+ * Outputs as gptst_gproj_bwd.  (The default path reaches this kernel through gptst_hypertem_dw.)                              */
 int gptst_gproj3_bwd(const float* dY, const void* mask, const float* X, const float* W, float* dX, float* dW_part,
                      float* dbias_part, float* dRes, int G, int R, long group_stride, long row_stride, int D, int act, int prec,
                      int splits, int flags, void* stream);
-/* EXPERIMENTAL companion of gptst_gproj3_bwd for hyperTem (csrc/tmix3.cu; not used by the Python side yet): gptst_tmix_bwd with the
- * residual gradient rebuilt in the kernel, dx_out = dout * act'(mask) + M^T o dy (written, not accumulated), so that the projection
- * backward can skip its dRes store (dRes = NULL).  mask as written by gptst_gproj3_fwd, or NULL for act' = 1.                       */
-int gptst_tmix3_bwd(const float* dy, const float* x, const float* M, const float* dout, const void* mask, float* dx_out,
-                    float* dM_part, int B, int T, int N, int D, int prec, int splits, void* stream);
 /* decoder output projection dim_flow_out = nn.Linear(D, O), O = input_base_dim <= 4 (GPTST.py:454-458), replacing
  * `self.dim_flow_out(flow_decode)` and its autograd: y (rows,O) = x (rows,D) W^T + b, W (O,D) as nn.Linear stores it, D = 64|128.
  * Backward in one pass: dX (rows,D) = dy W (may be NULL) and part (parts, O*D + O) = per-CTA partials of dW = dy^T x

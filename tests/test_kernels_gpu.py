@@ -534,27 +534,3 @@ def test_deferred_partial_sums_through_tables():
         assert_close(a, b.double().cpu(), atol=scale_tol(b, 1e-6), rtol=0.0, what="deferred partial sums")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GPTST_B200_EXPERIMENTAL", "0") != "1",
-                    reason="experimental kernels (csrc/gproj3.cu) are opt-in: set GPTST_B200_EXPERIMENTAL=1")
-@pytest.mark.parametrize("tmix3", ["0", "1"])
-@pytest.mark.parametrize("B,N", [(2, 23), (2, 170), (3, 207)])
-def test_hypertem_block_with_sign_mask_projection(B, N, tmix3, monkeypatch):
-    """GPTST_B200_GPROJ3=1: hyperTem through the sign-mask projection kernels gives the default path's outputs and gradients
-    (kernel-level agreement on the B200: profiles/gproj3_check_r01.log)."""
-    from gptst_b200 import ops
-    D, T = 64, 12
-    g = torch.Generator(device="cuda").manual_seed(9)
-    mk = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc)
-    eb, Mn, W, b, go = mk(B, T, N, D), mk(N, T, T, sc=0.2), mk(B, T, D, D, sc=D ** -0.5), mk(B, T, D), mk(B, T, N, D, sc=0.01)
-
-    def run(flag):
-        monkeypatch.setenv("GPTST_B200_GPROJ3", flag)
-        monkeypatch.setenv("GPTST_B200_TMIX3", tmix3 if flag == "1" else "0")
-        ins = [t.clone().requires_grad_() for t in (eb, Mn, W, b)]
-        out = ops.hypertem_core(*ins, 3)
-        out.backward(go)
-        return [out.detach()] + [t.grad for t in ins]
-
-    ref, got = run("0"), run("1")
-    for name, a, r in zip(("out", "d eb", "d Mn", "d W", "d bias"), got, ref):
-        assert_close(a, r.double().cpu(), atol=scale_tol(r, 2e-6), rtol=0.0, what="gproj3 hyperTem " + name)

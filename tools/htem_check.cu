@@ -94,6 +94,8 @@ static int run_case(void* L, int B, int N, float xscale, float gscale, bool timi
     pack_t pack = (pack_t)dlsym(L, "gptst_hypertem_pack_w");
     hfwd_t hfwd = (hfwd_t)dlsym(L, "gptst_hypertem_fwd");
     hbwd_t hbwd = (hbwd_t)dlsym(L, "gptst_hypertem_bwd");
+    hfwd_t hfwd_ws = (hfwd_t)dlsym(L, "gptst_hypertem_fwd_ws");
+    hbwd_t hbwd_ws = (hbwd_t)dlsym(L, "gptst_hypertem_bwd_ws");
     if (!tmix || !fwd2 || !bwd2 || !tmixb || !tsplits_f || !splits_f || !wbytes || !pack || !hfwd || !hbwd) { printf("missing symbol\n"); return 1; }
     const int T = 12, D = 64, ROT = timing ? 4 : 1;
     const int Npad = (N + 15) / 16 * 16;
@@ -135,6 +137,23 @@ static int run_case(void* L, int B, int N, float xscale, float gscale, bool timi
     CK(cudaMemcpy(&bad, g_out + 2, 4, cudaMemcpyDeviceToHost));
     printf("    sign-mask bits that disagree with (out > 0): %u of %zu\n", bad, A);
 
+    if (hfwd_ws) {       // warp-specialised variant against the same reference
+        float *o3, *r3;
+        uint2* m3;
+        CK(cudaMalloc(&o3, A * 4)); CK(cudaMalloc(&r3, A * 4)); CK(cudaMalloc(&m3, ((size_t)G * Npad + 16) * 8));
+        CK(cudaMemset(o3, 0xff, A * 4)); CK(cudaMemset(r3, 0xff, A * 4)); CK(cudaMemset(m3, 0, ((size_t)G * Npad + 16) * 8));
+        const int rcw = hfwd_ws(eb[0], Mn, wf, bias, o3, m3, r3, B, T, N, D, 0);
+        CK(cudaDeviceSynchronize());
+        printf("  forward (warp-specialised) rc=%d\n", rcw);
+        report("ret ws", r3, ret2, A);
+        report("out ws", o3, out2, A);
+        CK(cudaMemset(g_out + 2, 0, 4));
+        mask_check<<<592, 256>>>(o3, m3, G, N, Npad, g_out + 2);
+        CK(cudaMemcpy(&bad, g_out + 2, 4, cudaMemcpyDeviceToHost));
+        printf("    sign-mask bits (ws) that disagree with (out > 0): %u of %zu\n", bad, A);
+        cudaFree(o3); cudaFree(r3); cudaFree(m3);
+    }
+
     // reference backward: projection backward (dret, dRes = dy) then the fused mix backward accumulates into dRes
     rc = bwd2(dO[0], out2, ret2, W, dX2, dW2, db2, dR2, G, N, (long)N * D, (long)D, D, 1, 3, sp, 0);
     CK(cudaDeviceSynchronize());
@@ -145,6 +164,17 @@ static int run_case(void* L, int B, int N, float xscale, float gscale, bool timi
     CK(cudaDeviceSynchronize());
     printf("  backward rc ref=%d fused=%d\n", rc, rcf);
     report("deb", deb[0], dR2, A);
+    if (hbwd_ws) {
+        float *d3, *dr3;
+        CK(cudaMalloc(&d3, A * 4)); CK(cudaMalloc(&dr3, A * 4));
+        CK(cudaMemset(d3, 0xff, A * 4)); CK(cudaMemset(dr3, 0xff, A * 4));
+        const int rcw = hbwd_ws(dO[0], mask, Mn, wb, d3, dr3, B, T, N, D, 0);
+        CK(cudaDeviceSynchronize());
+        printf("  backward (warp-specialised) rc=%d\n", rcw);
+        report("dret ws", dr3, dret[0], A);
+        report("deb ws", d3, dR2, A);
+        cudaFree(d3); cudaFree(dr3);
+    }
 
     if (timing) {
         const float tp = time_it([&](int) { pack(W, wf, wb, G, 0); }, 20);
@@ -156,6 +186,16 @@ static int run_case(void* L, int B, int N, float xscale, float gscale, bool timi
                                                    tmixb(dX2, eb[i % ROT], Mn, deb[i % ROT], dM2, B, T, N, D, 3, spm, 0); }, 20);
         const float t_b = time_it([&](int i) { hbwd(dO[i % ROT], mask, Mn, wb, deb[i % ROT], 0, B, T, N, D, 0); }, 40);
         const float t_br = time_it([&](int i) { hbwd(dO[i % ROT], mask, Mn, wb, deb[i % ROT], dret[i % ROT], B, T, N, D, 0); }, 40);
+        if (hfwd_ws) {
+            const float t_w = time_it([&](int i) { hfwd_ws(eb[i % ROT], Mn, wf, bias, out[i % ROT], mask, 0, B, T, N, D, 0); }, 40);
+            const float t_wr = time_it([&](int i) { hfwd_ws(eb[i % ROT], Mn, wf, bias, out[i % ROT], mask, ret[i % ROT], B, T, N, D, 0); }, 40);
+            printf("  time (us): fwd warp-specialised %.1f (%.0f GB/s of 2A)  +ret %.1f\n", t_w, 2 * (double)A * 4 / t_w * 1e-3, t_wr);
+        }
+        if (hbwd_ws) {
+            const float t_w = time_it([&](int i) { hbwd_ws(dO[i % ROT], mask, Mn, wb, deb[i % ROT], 0, B, T, N, D, 0); }, 40);
+            const float t_wr = time_it([&](int i) { hbwd_ws(dO[i % ROT], mask, Mn, wb, deb[i % ROT], dret[i % ROT], B, T, N, D, 0); }, 40);
+            printf("  time (us): bwd warp-specialised %.1f (%.0f GB/s of 2A)  +dret %.1f\n", t_w, 2 * (double)A * 4 / t_w * 1e-3, t_wr);
+        }
         CK(cudaDeviceSynchronize());
         const double Ab = (double)A * 4;
         printf("  time (us): pack %.1f | fwd ref (tmix+gproj) %.1f  fused %.1f (%.0f GB/s of 2A)  fused+ret %.1f | bwd ref (gproj_bwd+tmix_bwd) %.1f  "

@@ -19,7 +19,6 @@ typedef const float* cf;
 typedef int (*gproj_fwd_t)(cf, cf, cf, cf, float*, int, int, long, long, int, int, int, void*);
 typedef int (*gproj_splits_t)(int, int, int);
 typedef int (*gproj_bwd_t)(cf, cf, cf, cf, float*, float*, float*, float*, int, int, long, long, int, int, int, int, void*);
-typedef int (*gproj3_fwd_t)(cf, cf, cf, cf, float*, void*, int, int, long, long, int, int, int, void*);
 typedef int (*gproj3_bwd_t)(cf, const void*, cf, cf, float*, float*, float*, float*, int, int, long, long, int, int, int, int, int, void*);
 typedef int (*tmix_t)(cf, cf, float*, int, int, int, int, int, int, void*);
 typedef int (*tmix_bwd_splits_t)(int, int);
@@ -27,7 +26,12 @@ typedef int (*tmix_bwd_t)(cf, cf, cf, float*, float*, int, int, int, int, int, i
 typedef int (*cap_route_fwd_t)(cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, int, void*);
 typedef int (*cap_hop_e1_t)(cf, cf, float*, int, int, int, int, int, void*);
 typedef int (*cap_recon_hop_t)(cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, void*);
-typedef cap_recon_hop_t cap_recon_hop3_t;
+typedef long (*hypertem_wfrag_bytes_t)(int);
+typedef int (*hypertem_pack_w_t)(cf, void*, void*, int, void*);
+typedef int (*hypertem_fwd_t)(cf, cf, const void*, cf, float*, void*, float*, int, int, int, int, void*);
+typedef int (*hypertem_bwd_t)(cf, const void*, cf, const void*, float*, float*, int, int, int, int, void*);
+typedef int (*hypertem_dw_t)(cf, const void*, cf, float*, float*, int, int, int, int, int, int, void*);
+typedef int (*tmix_dM2_t)(cf, cf, float*, int, int, int, int, int, void*);
 typedef int (*cap_dv_dcr_hoprows_t)(cf, cf, cf, cf, cf, cf, float*, float*, float*, int, int, int, int, int, int, void*);
 typedef int (*cap_hop_bwd_parts_t)(int);
 typedef int (*cap_hop_bwd_cols_t)(cf, cf, cf, cf, cf, float*, float*, int, int, int, int, int, void*);
@@ -82,10 +86,11 @@ int main(int argc, char** argv) {
     const int T = 12, D = 64, H = 10, HT = 16, RT = 2, prec = 3, K = T * H;
     void* L = dlopen("gpt-st_b200/libgptst_b200.so", RTLD_NOW);
     if (!L) { printf("dlopen failed: %s\n", dlerror()); return 1; }
-    SYM(gproj_fwd) SYM(gproj_splits) SYM(gproj_bwd) SYM(gproj3_fwd) SYM(gproj3_bwd) SYM(tmix) SYM(tmix_bwd_splits) SYM(tmix_bwd)
-    SYM(cap_route_fwd) SYM(cap_hop_e1) SYM(cap_recon_hop) SYM(cap_recon_hop3) SYM(cap_dv_dcr_hoprows) SYM(cap_hop_bwd_parts) SYM(cap_hop_bwd_cols)
+    SYM(gproj_fwd) SYM(gproj_splits) SYM(gproj_bwd) SYM(gproj3_bwd) SYM(tmix) SYM(tmix_bwd_splits) SYM(tmix_bwd)
+    SYM(cap_route_fwd) SYM(cap_hop_e1) SYM(cap_recon_hop) SYM(cap_dv_dcr_hoprows) SYM(cap_hop_bwd_parts) SYM(cap_hop_bwd_cols)
     SYM(cap_route_bwd_dz) SYM(linear_bwd_acc_splits) SYM(linear_bwd_acc) SYM(proj_out_fwd) SYM(proj_out_bwd_parts) SYM(proj_out_bwd)
     SYM(score_head_fwd)
+    SYM(hypertem_wfrag_bytes) SYM(hypertem_pack_w) SYM(hypertem_fwd) SYM(hypertem_bwd) SYM(hypertem_dw) SYM(tmix_dM2)
 
     const size_t M = (size_t)B * T * N, A = M * D, C = M * H, S = (size_t)B * T * H * D;
     const double Ab = A * 4.0, Cb = C * 4.0;
@@ -116,7 +121,7 @@ int main(int argc, char** argv) {
         q.c = dev(C); q.s = dev(S); q.e1 = dev((size_t)B * HT * D); q.v = dev(S); q.recon = dev(A); q.out_n = dev(A);
         q.drecon = dev(A); q.dx = dev(A); q.dcr = dev(C); q.dr = dev(S); q.dp2 = dev(S); q.ds = dev(S); q.dZ = dev(A); q.ddadj = dev(C);
         q.y1 = dev(M); q.dy1 = dev(M, 300 + i, 0.01f);
-        CK(cudaMalloc(&q.mask, M * 8));
+        CK(cudaMalloc(&q.mask, ((size_t)B * T * ((N + 15) / 16 * 16) + 16) * 8)); CK(cudaMemset(q.mask, 0xff, ((size_t)B * T * ((N + 15) / 16 * 16) + 16) * 8));
     }
     CK(cudaDeviceSynchronize());
     const long gsT = (long)N * D, rsT = D, gsN = D, rsN = (long)N * D;
@@ -124,23 +129,31 @@ int main(int argc, char** argv) {
     printf("---- hyperTem (GPTST.py:154-163)\n");
     bench("tmix                       fwd", 2 * Ab, iters, [&](int i) { return tmix(st[i].x, Mn, st[i].ret, B, T, N, D, 0, 0, 0); });
     bench("gproj time-grouped         fwd", 3 * Ab, iters, [&](int i) { return gproj_fwd(st[i].ret, Wbt, bbt, st[i].x, st[i].out_t, B * T, N, gsT, rsT, D, 1, prec, 0); });
-    bench("gproj3 time-grouped + mask fwd (experimental)", 3 * Ab, iters, [&](int i) { return gproj3_fwd(st[i].ret, Wbt, bbt, st[i].x, st[i].out_t, st[i].mask, B * T, N, gsT, rsT, D, 1, prec, 0); });
     bench("gproj time-grouped         bwd", 5 * Ab, iters, [&](int i) { return gproj_bwd(st[i].dout, st[i].out_t, st[i].ret, Wbt, st[i].dret, dWt, dbt, st[i].deb, B * T, N, gsT, rsT, D, 1, prec, sp_t, 0); });
-    bench("gproj3 time-grouped, mask  bwd (experimental)", 4 * Ab, iters, [&](int i) { return gproj3_bwd(st[i].dout, st[i].mask, st[i].ret, Wbt, st[i].dret, dWt, dbt, st[i].deb, B * T, N, gsT, rsT, D, 1, prec, sp_t, 0, 0); });
     bench("tmix_bwd (dx += M^T dy, dM) bwd", 4 * Ab, iters, [&](int i) { return tmix_bwd(st[i].dret, st[i].x, Mn, st[i].deb, dMp, B, T, N, D, prec, sp_m, 0); });
 
+    {   // the fused block (csrc/htem_fused.cu): main-chain kernels + the two side-stream parameter-gradient kernels
+        void *wf, *wb;
+        CK(cudaMalloc(&wf, hypertem_wfrag_bytes(B * T))); CK(cudaMalloc(&wb, hypertem_wfrag_bytes(B * T)));
+        const int npad = (N + 15) / 16 * 16;
+        bench("hypertem pack_w (side stream)  ", 3 * (double)B * T * D * D * 4, iters, [&](int i) { return hypertem_pack_w(Wbt, wf, wb, B * T, 0); });
+        bench("hypertem FUSED fwd (+mask,+ret)", 3 * Ab, iters, [&](int i) { return hypertem_fwd(st[i].x, Mn, wf, bbt, st[i].out_t, st[i].mask, st[i].ret, B, T, N, D, 0); });
+        bench("hypertem FUSED fwd (no ret)    ", 2 * Ab, iters, [&](int i) { return hypertem_fwd(st[i].x, Mn, wf, bbt, st[i].out_t, st[i].mask, 0, B, T, N, D, 0); });
+        bench("hypertem FUSED bwd (+dret)     ", 3 * Ab, iters, [&](int i) { return hypertem_bwd(st[i].dout, st[i].mask, Mn, wb, st[i].deb, st[i].dret, B, T, N, D, 0); });
+        bench("hypertem dW_bt/db_bt (side)    ", 2 * Ab, iters, [&](int i) { return hypertem_dw(st[i].dout, st[i].mask, st[i].ret, dWt, dbt, B, T, N, D, npad, sp_t, 0); });
+        bench("hypertem dM_n (side)           ", 2 * Ab, iters, [&](int i) { return tmix_dM2(st[i].dret, st[i].x, dMp, B, T, N, D, sp_m, 0); });
+    }
     printf("---- cap (GPTST.py:100-141)\n");
     bench("cap_route_fwd (routing)    fwd", Ab + 2 * Cb, iters, [&](int i) { return cap_route_fwd(st[i].x, Wp, bp, dadj, st[i].c, st[i].s, B, T, N, D, H, RT, prec, 0); });
     bench("cap_hop_e1                 fwd", 0.1 * Ab, iters, [&](int i) { return cap_hop_e1(st[i].s, dyn, st[i].e1, B, T, D, H, HT, 0); });
     bench("cap_recon_hop              fwd", Ab + Cb, iters, [&](int i) { return cap_recon_hop(st[i].c, st[i].s, dyn, st[i].e1, st[i].v, st[i].recon, B, T, N, D, H, HT, 0); });
-    bench("cap_recon_hop3             fwd (experimental)", Ab + Cb, iters, [&](int i) { return cap_recon_hop3(st[i].c, st[i].s, dyn, st[i].e1, st[i].v, st[i].recon, B, T, N, D, H, HT, 0); });
     bench("gproj node-grouped         fwd", 3 * Ab, iters, [&](int i) { return gproj_fwd(st[i].recon, Wn, bn, st[i].x, st[i].out_n, N, B * T, gsN, rsN, D, 1, prec, 0); });
     bench("gproj node-grouped         bwd", 5 * Ab, iters, [&](int i) { return gproj_bwd(st[i].dout, st[i].out_n, st[i].recon, Wn, st[i].drecon, dWnp, dbnp, st[i].dx, N, B * T, gsN, rsN, D, 1, prec, sp_n, 0); });
     bench("cap_dv_dcr_hoprows         bwd", Ab + 2 * Cb, iters, [&](int i) { return cap_dv_dcr_hoprows(st[i].c, st[i].v, st[i].drecon, st[i].s, dyn, st[i].e1, st[i].dcr, st[i].dr, st[i].dp2, B, T, N, D, H, HT, 0); });
     bench("cap_hop_bwd_cols           bwd", 0.3 * Ab, iters, [&](int i) { return cap_hop_bwd_cols(st[i].s, dyn, st[i].e1, st[i].dr, st[i].dp2, st[i].ds, ddynp, B, T, D, H, HT, 0); });
     bench("cap_route_bwd_dz           bwd", 2 * Ab + 3 * Cb, iters, [&](int i) { return cap_route_bwd_dz(st[i].x, Wp, bp, st[i].c, st[i].ds, st[i].dcr, st[i].dZ, st[i].ddadj, B, T, N, D, H, prec, 0); });
     bench("linear_bwd_acc (ln_p)      bwd", 4 * Ab, iters, [&](int i) { return linear_bwd_acc(st[i].dZ, st[i].x, Wp, st[i].dx, dWpp, dbpp, (long)M, D, prec, sp_l, 0); });
-    bench("gproj3 shared weight       bwd (experimental)", 4 * Ab, iters, [&](int i) { return gproj3_bwd(st[i].dZ, 0, st[i].x, Wp, st[i].dx, dWpp, dbpp, 0, 1, (int)M, 0L, (long)D, D, 0, prec, sp_l, 3, 0); });
+    bench("gproj3 shared weight       bwd (sign-mask kernel)", 4 * Ab, iters, [&](int i) { return gproj3_bwd(st[i].dZ, 0, st[i].x, Wp, st[i].dx, dWpp, dbpp, 0, 1, (int)M, 0L, (long)D, D, 0, prec, sp_l, 3, 0); });
 
     printf("---- heads\n");
     bench("proj_out (dim_flow_out)    fwd", Ab, iters, [&](int i) { return proj_out_fwd(st[i].out_n, Wo, bo, st[i].y1, (long)M, D, 1, 0); });
