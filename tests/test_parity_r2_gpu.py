@@ -265,3 +265,21 @@ def test_cap_block_fp16_range(xs, gs):
     for k in ins:
         assert torch.isfinite(c[k].grad).all(), k
         assert_close(c[k].grad, ins[k].grad, atol=tol(ins[k].grad, 3e-4), rtol=0, what=f"cap grad {k} at |x|~{xs:g}, |g|~{gs:g}")
+
+
+def test_nccl_gradients_equal_single_gpu():
+    """1-vs-2-GPU gradient equality on the real model over NCCL (tools/dp_grad_check.py under torchrun); needs two GPUs."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run by `gpurun --gpus 2`; log committed as profiles/dp_grad_check_r02.log)")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for epoch in ("1", "200"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29631", os.path.join(repo, "tools", "dp_grad_check.py"), epoch],
+                           capture_output=True, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+        d = json.loads(line[-1])
+        assert d["ok"] and d["worst_rel_grad_err_vs_single_gpu"] <= 2e-6 and d["param_max_diff_across_ranks_after_7_graph_steps"] == 0.0
