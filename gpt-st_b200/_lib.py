@@ -79,6 +79,14 @@ SIGNATURES = {
                                 C.c_float, _f]),
     "gptst_opt_chunk": (_i, []),
     "gptst_adam_clip": (_i, [_f, _f, _i, _f, _f, _f, _f, _f]),
+    "gptst_glu_tconv_fwd": (_i, [_f] * 8 + [_i] * 6 + [_f]),
+    "gptst_tconv_fwd": (_i, [_f] * 4 + [_i] * 6 + [_f]),
+    "gptst_glu_gate_bwd": (_i, [_f] * 4 + [_i] * 4 + [_f]),
+    "gptst_tconv_dw_splits": (_i, [_i] * 4),
+    "gptst_tconv_dw": (_i, [_f] * 4 + [_i] * 7 + [_f]),
+    "gptst_gate_fwd": (_i, [_f] * 7 + [_l, _i, _i, _f]),
+    "gptst_gate_blend": (_i, [_f] * 6 + [_l, _f]),
+    "gptst_gate_bwd": (_i, [_f] * 7 + [_l, _f]),
     "gptst_version": (C.c_char_p, []),
 }
 

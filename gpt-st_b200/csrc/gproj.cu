@@ -278,7 +278,7 @@ cudaError_t gproj_bwd_umma(const float* dY, const float* Y, const float* X, cons
 // second generation for D = 64 (gproj2.cu): fp16-split mma.sync m16n8k16, forward and backward
 int gproj2_splits(int G, int R);
 cudaError_t gproj2_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R, long gs,
-                       long rs, int act, int prec, cudaStream_t st);
+                       long rs, int act, int prec, cudaStream_t st, const float* Gate = nullptr, float* Zout = nullptr);
 cudaError_t gproj2_bwd(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,
                        float* dRes, int G, int R, long gs, long rs, int act, int prec, int splits, int flags, cudaStream_t st);
 // GPTST_B200_GPROJ = "umma" (tcgen05 forward) | "mma" (first-generation tf32 mma.sync) select the older kernels (A/B testing)
@@ -339,6 +339,16 @@ extern "C" int gptst_gproj_fwd(const float* X, const float* W, const float* bias
     DISPATCH_D_PREC(D, prec, CALL);
 #undef CALL
     return -2;
+}
+
+// Fusion gate of the eval path (reference model/Model.py:12-17) as the epilogue of its second product, D = 64:
+//   z = sigmoid(time W + bias + xs),  h = z * flow + (1 - z) * time      (xs = HS_fc(flow), computed by a plain gptst_gproj_fwd)
+// W is [in][out] (one group); z (rows, D) is kept for gptst_gate_bwd when non-null.  Other widths: -2 (use gptst_gate_blend).
+extern "C" int gptst_gate_fwd(const float* flow, const float* time, const float* xs, const float* W, const float* bias,
+                              float* h, float* z, long rows, int D, int prec, void* stream) {
+    if (!flow || !time || !xs || !W || !h || rows <= 0) return -1;
+    if (rows > 0x7fffffffL || !use_gp2(D, prec)) return -2;
+    return (int)gproj2_fwd(time, W, bias, xs, h, 1, (int)rows, 0, D, 2, prec, (cudaStream_t)stream, flow, z);
 }
 
 extern "C" int gptst_gproj_bwd(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dW_part,

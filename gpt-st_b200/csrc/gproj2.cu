@@ -48,7 +48,10 @@ __device__ __forceinline__ int kperm(int j) {   // physical k (mod 16) -> logica
 template <int NW, int MINB, int PREC>
 __global__ void __launch_bounds__(NW * 32, MINB)
 gproj2_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
-                  const float* __restrict__ Res, float* __restrict__ Y, int R, long gs, long rs, int act, int chunks) {
+                  const float* __restrict__ Res, float* __restrict__ Y, int R, long gs, long rs, int act, int chunks,
+                  const float* __restrict__ Gate, float* __restrict__ Zout) {
+    // act: 0 none, 1 LeakyReLU, 2 fusion gate (reference model/Model.py:12-17): z = sigmoid(X W + b + Res),
+    //      Y = z * Gate + (1 - z) * X   (X = the operand rows themselves, still fp32 in shared memory), z -> Zout if given
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned char* Xs = smraw;                                   // [NW*16][ROWB]
     unsigned char* Wt = Xs + (size_t)NW * 16 * ROWB;             // [64][ROWB]  W_g planes, row = logical k
@@ -130,7 +133,15 @@ gproj2_fwd_kernel(const float* __restrict__ X, const float* __restrict__ W, cons
                     const float2 rr = *reinterpret_cast<const float2*>(Rs + (size_t)rl * ROWB + col * 4);
                     y0 += rr.x; y1 += rr.y;
                 }
-                if (act) { y0 = lrelu(y0); y1 = lrelu(y1); }
+                if (act == 1) { y0 = lrelu(y0); y1 = lrelu(y1); }
+                else if (act == 2) {
+                    const float z0 = 1.f / (1.f + expf(-y0)), z1 = 1.f / (1.f + expf(-y1));
+                    const float2 xr = *reinterpret_cast<const float2*>(Xs + (size_t)rl * ROWB + col * 4);
+                    const float2 fr = *reinterpret_cast<const float2*>(Gate + (long)grp * gs + (long)rg * rs + col);
+                    if (Zout) *reinterpret_cast<float2*>(Zout + (long)grp * gs + (long)rg * rs + col) = make_float2(z0, z1);
+                    y0 = z0 * fr.x + (1.f - z0) * xr.x;
+                    y1 = z1 * fr.y + (1.f - z1) * xr.y;
+                }
                 *reinterpret_cast<float2*>(Yg + (long)rg * rs + col) = make_float2(y0, y1);
             }
         }
@@ -454,13 +465,13 @@ static int pick_nw(int R) {   // warps (= 16-row tiles) per CTA chunk
 
 template <int NW, int MINB, int PREC>
 static cudaError_t launch_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R,
-                              long gs, long rs, int act, cudaStream_t st) {
+                              long gs, long rs, int act, const float* Gate, float* Zout, cudaStream_t st) {
     const int chunks = (R + NW * 16 - 1) / (NW * 16);
     const size_t smem = (size_t)NW * 16 * ROWB * (Res ? 2 : 1) + (size_t)D * ROWB + D * 4;
     auto kern = gproj2_fwd_kernel<NW, MINB, PREC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(unsigned)((size_t)G * chunks), NW * 32, smem, st>>>(X, W, bias, Res, Y, R, gs, rs, act, chunks);
+    kern<<<(unsigned)((size_t)G * chunks), NW * 32, smem, st>>>(X, W, bias, Res, Y, R, gs, rs, act, chunks, Gate, Zout);
     return cudaGetLastError();
 }
 
@@ -489,8 +500,8 @@ static cudaError_t launch_bwd(const float* dY, const float* Y, const float* X, c
 
 template <int PREC>
 static cudaError_t fwd_p(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R, long gs,
-                         long rs, int act, cudaStream_t st) {
-    GP2_DISPATCH(launch_fwd, X, W, bias, Res, Y, G, R, gs, rs, act, st)
+                         long rs, int act, const float* Gate, float* Zout, cudaStream_t st) {
+    GP2_DISPATCH(launch_fwd, X, W, bias, Res, Y, G, R, gs, rs, act, Gate, Zout, st)
 }
 template <int PREC>
 static cudaError_t bwd_p(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,
@@ -518,9 +529,10 @@ int gproj2_splits(int G, int R) {
 }
 
 cudaError_t gproj2_fwd(const float* X, const float* W, const float* bias, const float* Res, float* Y, int G, int R, long gs,
-                       long rs, int act, int prec, cudaStream_t st) {
-    if (prec == PREC_3XTF32) return gp2::fwd_p<PREC_3XTF32>(X, W, bias, Res, Y, G, R, gs, rs, act, st);
-    return gp2::fwd_p<PREC_TF32>(X, W, bias, Res, Y, G, R, gs, rs, act, st);
+                       long rs, int act, int prec, cudaStream_t st, const float* Gate, float* Zout) {
+    if (act == 2 && !Gate) return cudaErrorInvalidValue;
+    if (prec == PREC_3XTF32) return gp2::fwd_p<PREC_3XTF32>(X, W, bias, Res, Y, G, R, gs, rs, act, Gate, Zout, st);
+    return gp2::fwd_p<PREC_TF32>(X, W, bias, Res, Y, G, R, gs, rs, act, Gate, Zout, st);
 }
 
 cudaError_t gproj2_bwd(const float* dY, const float* Y, const float* X, const float* W, float* dX, float* dWp, float* dbp,

@@ -234,6 +234,39 @@ int gptst_opt_chunk(void);
 int gptst_adam_clip(const void* table, const void* block_map, int nblocks, float* partial, int* step, const float* hyper,
                     float* norm_out, void* stream);
 
+/* ---- eval-path glue next to the encoder ----------------------------------------------
+ * Fusion gate of Enhance_model (reference model/Model.py:12-17, called from Model.py:106-109):
+ *     z = sigmoid(HS_fc(flow) + HT_fc(time)),  h = z * flow + (1 - z) * time          (then output_fc(h))
+ * gptst_gate_fwd replaces lines 13-16 with ONE launch: the second product HT_fc(time) with the sigmoid and the blend as its
+ * epilogue (D = 64, three-term split); xs = HS_fc(flow) comes from a plain gptst_gproj_fwd, W is HT_fc.weight^T ([in][out]),
+ * z (rows, D) is kept for the backward when non-NULL.  gptst_gate_blend is the same gate as an elementwise kernel on the two
+ * pre-activations (any width; n elements, n % 4 == 0); gptst_gate_bwd gives dpre = dh (flow - time) z (1 - z) (the gradient of both
+ * pre-activations), dx = dh z (direct path into flow) and dy = dh (1 - z) (direct path into time).                               */
+int gptst_gate_fwd(const float* flow, const float* time, const float* xs, const float* W, const float* bias, float* h, float* z,
+                   long rows, int D, int prec, void* stream);
+int gptst_gate_blend(const float* xs, const float* xt, const float* x, const float* y, float* h, float* z, long n, void* stream);
+int gptst_gate_bwd(const float* dh, const float* z, const float* x, const float* y, float* dpre, float* dx, float* dy, long n,
+                   void* stream);
+/* STGCN's gated (GLU) temporal convolution, reference model/STGCN/stgcn.py:25-53 (TemporalConvLayer, act = "GLU") with the
+ * Align of stgcn.py:10-23 folded in:  out = (conv(x)[:, :Cout] + align(x)) * sigmoid(conv(x)[:, Cout:]),
+ * conv = Conv2d(Cin, 2 Cout, (kt, 1), padding (kt-1)/2).  x (B, Cin, T, N) and out (B, Cout, T, N) in the reference's own layout
+ * (N fastest), W (2 Cout, Cin, kt) = conv.weight without its trailing 1, bias (2 Cout); aw (Cout, Cin) / ab (Cout) = the 1x1
+ * Align conv, only when Cin > Cout (NULL otherwise; Cin < Cout zero-pads the channels, Cin == Cout is the identity).
+ * kt odd (an even kt shortens the sequence and the reference's own residual add fails), T <= 12.  P = conv[:, :Cout] + align(x)
+ * and S = sigmoid(conv[:, Cout:]) are stored for the backward when both are non-NULL.
+ * Backward pieces: gptst_glu_gate_bwd: dconv (B, 2 Cout, T, N) = [dout S ; dout P S (1 - S)];
+ * gptst_tconv_fwd: plain "same"-padded temporal convolution (used for dx = conv of dconv with the flipped, transposed weights,
+ * the Align term folded into the centre tap by the caller); gptst_tconv_dw: per-split partials dW_part (splits, C2, Cin, kt),
+ * db_part (splits, C2) of dW[o,i,k] = sum dconv[b,o,t,n] x[b,i,t+k-pad,n], db[o] = sum dconv, splits = gptst_tconv_dw_splits().   */
+int gptst_glu_tconv_fwd(const float* x, const float* W, const float* bias, const float* aw, const float* ab, float* out, float* P,
+                        float* S, int B, int Cin, int Cout, int T, int N, int kt, void* stream);
+int gptst_tconv_fwd(const float* x, const float* W, const float* bias, float* out, int B, int Cin, int Cout, int T, int N, int kt,
+                    void* stream);
+int gptst_glu_gate_bwd(const float* dout, const float* P, const float* S, float* dconv, int B, int Cout, int T, int N, void* stream);
+int gptst_tconv_dw_splits(int B, int C2, int Cin, int N);
+int gptst_tconv_dw(const float* dconv, const float* x, float* dW_part, float* db_part, int B, int C2, int Cin, int T, int N, int kt,
+                   int splits, void* stream);
+
 /* library identification: "gptst_b200 <version> sm_100a" */
 const char* gptst_version(void);
 

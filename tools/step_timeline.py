@@ -1,6 +1,6 @@
 """Timeline of ONE graph-replayed pre-training step (torch.profiler / CUPTI): start offset, duration and stream of
 every kernel, written as CSV so the critical path can be read offline.
-usage: python tools/step_timeline.py [out.csv] [epoch=200]"""
+usage: python tools/step_timeline.py [out.csv] [epoch=200] [workload=pems08] [batch]"""
 import os, sys, re
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,9 @@ from gptst_b200.train import PretrainStep
 
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/step_timeline.csv"
 epoch = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-N, D, B = bench.WORKLOADS["pems08"]
+N, D, B = bench.WORKLOADS[sys.argv[3] if len(sys.argv) > 3 else "pems08"]
+if len(sys.argv) > 4:
+    B = int(sys.argv[4])
 model = GPTST_Model(bench.make_cfg(N, D, "cuda")).cuda()
 bench.run_init(model, 0)
 step = PretrainStep(model)
