@@ -106,19 +106,21 @@ class cap(nn.Module):
         Wn = ops.lowrank_table(node_embeddings, self.weights_spa)       # einsum("nd,dio->nio")
         bn = ops.lowrank_table(node_embeddings, self.bias_spa)
         if not dadj.is_cuda:
-            return dadj, dyn, Wn, bn, None
+            return dadj, dyn, Wn, bn, None, None
         # stride-0 (P, ...) views of the five parameter-side inputs: the block's backward returns its per-CTA gradient partials
         # for them and the sums run HERE (this stream) as the expands' backward, off the main chain (ops.expand_partials)
         B, T, H, N = dadj.shape
         exp = ops.cap_expand(self.ln_p.weight, self.ln_p.bias, dyn, Wn, bn, B, T, N, self.dim, H)
-        return dadj, dyn, Wn, bn, exp
+        # fragment-ordered fp16 copy of W_n for the fused reconstruction + projection kernel, packed here (off the main chain)
+        wnf = ops.cap_pack_wn(Wn) if ops.cap_fused_enabled(N, self.dim, H, T, ops.default_precision()) else None
+        return dadj, dyn, Wn, bn, exp, wnf
 
     def forward(self, x, node_embeddings, time_eb, teb, tables=None):
-        dadj, dyn, Wn, bn, exp = tables if tables is not None else self.tables(node_embeddings, time_eb, teb)
+        dadj, dyn, Wn, bn, exp, wnf = tables if tables is not None else self.tables(node_embeddings, time_eb, teb)
         if exp is None:
             out, c = ops.cap_core(x, self.ln_p.weight, self.ln_p.bias, dadj, dyn, Wn, bn, self.num_route)
         else:
-            out, c = ops.cap_core(x, exp[0], exp[1], dadj, exp[2], exp[3], exp[4], self.num_route, expanded=True)
+            out, c = ops.cap_core(x, exp[0], exp[1], dadj, exp[2], exp[3], exp[4], self.num_route, expanded=True, wnf=wnf)
         return out, c.unsqueeze(-1), dyn.detach()
 
 

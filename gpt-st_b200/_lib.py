@@ -79,6 +79,8 @@ SIGNATURES = {
                                 C.c_float, _f]),
     "gptst_opt_chunk": (_i, []),
     "gptst_adam_clip": (_i, [_f, _f, _i, _f, _f, _f, _f, _f]),
+    "gptst_cap_hop_ev": (_i, [_f] * 4 + [_i] * 5 + [_f]),
+    "gptst_cap_recon_proj": (_i, [_f] * 7 + [_i] * 5 + [_f]),
     "gptst_glu_tconv_fwd": (_i, [_f] * 8 + [_i] * 6 + [_f]),
     "gptst_tconv_fwd": (_i, [_f] * 4 + [_i] * 6 + [_f]),
     "gptst_glu_gate_bwd": (_i, [_f] * 4 + [_i] * 4 + [_f]),

@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 def build_tools(verbose: bool = True) -> None:
     """Stand-alone C++ checks under tools/ (kbench, htem_check): they dlopen the library, so they only need nvcc + libdl."""
     tools = os.path.join(os.path.dirname(HERE), "tools")
-    for name in ("kbench", "htem_check"):
+    for name in ("kbench", "htem_check", "cap_check"):
         src, exe = os.path.join(tools, name + ".cu"), os.path.join(tools, name)
         if os.path.isfile(exe) and os.path.getmtime(exe) >= os.path.getmtime(src):
             continue

@@ -387,9 +387,27 @@ def hypertem_core(eb, Mn, W, bias, prec=None):
 # ---------------------------------------------------------------------------------------------------
 # cap core
 # ---------------------------------------------------------------------------------------------------
+def cap_fused_enabled(N: int, D: int, H: int, T: int, prec: int) -> bool:
+    """Round-2 forward (hop in one launch, reconstruction fused into the node-adaptive projection): D = 64, N <= 256, T = 12,
+    three-term split.  GPTST_B200_CAP=split selects the four-launch chain (A/B runs, other geometries use it anyway)."""
+    return (D == 64 and T == 12 and prec == PREC_3XTF32 and os.environ.get("GPTST_B200_CAP", "fused") == "fused"
+            and bool(_lib.lib().gptst_cap_route2_supported(N, D, H)))
+
+
+def cap_pack_wn(Wn):
+    """Node-adaptive weights (N, 64, 64) [in][out] -> the fragment-ordered fp16 hi/lo table `gptst_cap_recon_proj` reads (no
+    gradient flows through it: the backward uses W_n itself).  Call it where W_n is produced (the block's table stream)."""
+    Wn = Wn.detach().contiguous()
+    _chk(Wn)
+    L = _lib.lib()
+    wf = torch.empty(L.gptst_hypertem_wfrag_bytes(Wn.shape[0]), dtype=torch.uint8, device=Wn.device)
+    _lib.check(L.gptst_hypertem_pack_w(_p(Wn), _p(wf), None, Wn.shape[0], _stream()), "gptst_hypertem_pack_w")
+    return wf
+
+
 class _CapCore(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, Wp_e, bp_e, dadj, dyn_e, Wn_e, bn_e, num_route, prec):
+    def forward(ctx, x, Wp_e, bp_e, dadj, dyn_e, Wn_e, bn_e, num_route, prec, wnf):
         x, dadj = x.contiguous(), dadj.contiguous()
         B, T, N, D = x.shape
         H, HT = dadj.shape[2], dyn_e.shape[2]
@@ -407,19 +425,32 @@ class _CapCore(torch.autograd.Function):
                                          prec, st), "gptst_cap_route_fwd")
         v = torch.empty_like(s)
         e1 = torch.empty((B, HT, D), device=x.device, dtype=torch.float32)
-        recon = torch.empty_like(x)
-        if os.environ.get("GPTST_B200_HOP", "split") == "fused":
-            # opt-in A/B variant: hop_e1 folded into recon_hop (one launch).  Measured SLOWER on the B200 (80 us vs 6.5 + 22 us:
-            # every slab CTA recomputes its sample's E1 out of L2), so the split pair stays the default.
-            _count(-1)
-            _lib.check(L.gptst_cap_recon_hop_fused(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
-                       "gptst_cap_recon_hop_fused")
+        need_grad = any(ctx.needs_input_grad[:7])
+        if cap_fused_enabled(N, D, H, T, prec):
+            # round 2: the hop in one launch, then reconstruction + node-adaptive projection + residual in one launch; `recon`
+            # is only written because the backward reads it (never in inference)
+            if wnf is None:
+                wnf = cap_pack_wn(Wn)
+            _lib.check(L.gptst_cap_hop_ev(_p(s), _p(dyn), _p(e1), _p(v), B, T, D, H, HT, st), "gptst_cap_hop_ev")
+            recon = torch.empty_like(x) if need_grad else None
+            out = torch.empty_like(x)
+            _lib.check(L.gptst_cap_recon_proj(_p(c), _p(v), _p(x), _p(wnf), _p(bn), _p(out), _p(recon), B, T, N, D, H, st),
+                       "gptst_cap_recon_proj")
         else:
-            _lib.check(L.gptst_cap_hop_e1(_p(s), _p(dyn), _p(e1), B, T, D, H, HT, st), "gptst_cap_hop_e1")
-            _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
-                       "gptst_cap_recon_hop")
-        out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
-        ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1)
+            recon = torch.empty_like(x)
+            if os.environ.get("GPTST_B200_HOP", "split") == "fused":
+                # opt-in A/B variant: hop_e1 folded into recon_hop (one launch).  Measured SLOWER on the B200 (80 us vs 6.5 + 22 us:
+                # every slab CTA recomputes its sample's E1 out of L2), so the split pair stays the default.
+                _count(-1)
+                _lib.check(L.gptst_cap_recon_hop_fused(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
+                           "gptst_cap_recon_hop_fused")
+            else:
+                _lib.check(L.gptst_cap_hop_e1(_p(s), _p(dyn), _p(e1), B, T, D, H, HT, st), "gptst_cap_hop_e1")
+                _lib.check(L.gptst_cap_recon_hop(_p(c), _p(s), _p(dyn), _p(e1), _p(v), _p(recon), B, T, N, D, H, HT, st),
+                           "gptst_cap_recon_hop")
+            out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
+        if need_grad:
+            ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1)
         ctx.prec = prec
         ctx.mark_non_differentiable(c)
         return out, c
@@ -472,7 +503,7 @@ class _CapCore(torch.autograd.Function):
                                              _p(dbp_part), B, T, N, D, H, ctx.prec, st), "gptst_cap_route_bwd")
         # the five partial buffers leave as they are: they are the gradients of the EXPANDED inputs, summed by the expands' own
         # backward on the stream that made them (see `expand_partials`)
-        return dx, dWp_part, dbp_part, ddadj, ddyn_part, dWn_part, dbn_part, None, None
+        return dx, dWp_part, dbp_part, ddadj, ddyn_part, dWn_part, dbn_part, None, None, None
 
 
 def cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, H):
@@ -481,15 +512,16 @@ def cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, H):
     return expand_partials_many((Wp, bp, dyn, Wn, bn), (p_wp, p_wp, p_dyn, p_wn, p_wn))
 
 
-def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None, expanded=False):
+def cap_core(x, Wp, bp, dadj, dyn, Wn, bn, num_route, prec=None, expanded=False, wnf=None):
     """x (B,T,N,D); Wp (D,D) [out,in]; dadj (B,T,H,N); dyn (B,HT,T*H); Wn (N,D,D); bn (N,D) -- or, with expanded=True, Wp, bp,
-    dyn, Wn, bn as returned by `cap_expand`.  Returns (out (B,T,N,D), c (B,T,H,N) non-differentiable)."""
+    dyn, Wn, bn as returned by `cap_expand`; wnf: `cap_pack_wn(Wn)` when the caller packed it ahead of time (else packed here).
+    Returns (out (B,T,N,D), c (B,T,H,N) non-differentiable)."""
     if not expanded:
         if not x.is_cuda:
             raise RuntimeError("gptst_b200 ops need CUDA tensors (no CPU fallback)")
         B, T, N, D = x.shape
         Wp, bp, dyn, Wn, bn = cap_expand(Wp, bp, dyn, Wn, bn, B, T, N, D, dadj.shape[2])
-    return _CapCore.apply(x, Wp, bp, dadj, dyn, Wn, bn, num_route, default_precision() if prec is None else prec)
+    return _CapCore.apply(x, Wp, bp, dadj, dyn, Wn, bn, num_route, default_precision() if prec is None else prec, wnf)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -234,6 +234,19 @@ int gptst_opt_chunk(void);
 int gptst_adam_clip(const void* table, const void* block_map, int nblocks, float* partial, int* step, const float* hyper,
                     float* norm_out, void* stream);
 
+/* ---- cap forward, round 2 (reference GPTST.py:125-141, D = 64, three-term split) ------------------------------------------
+ * gptst_cap_hop_ev: the whole inter-cluster hop (GPTST.py:125-134) in ONE launch, one CTA per sample:
+ *   e1 (B,HT,D) = LReLU(dyn_b (s_b + tau)),  v (B,T,H,D) = squash(LReLU(dyn_b^T e1) + s);  s (B,T,H,D), dyn (B,HT,T*H).
+ *   Replaces gptst_cap_hop_e1 + the first half of gptst_cap_recon_hop.
+ * gptst_cap_recon_proj = GPTST.py:135-141 in ONE launch: out = LReLU((c^T v) W_n + bias_n + x), W_n given as the fragment table
+ *   gptst_hypertem_pack_w(W_n, wfrag, NULL, N) writes (gptst_hypertem_wfrag_bytes(N) bytes); recon (B,T,N,D) = c^T v is stored
+ *   when non-NULL (the backward reads it).  Replaces the second half of gptst_cap_recon_hop + the node-grouped gptst_gproj_fwd:
+ *   `recon` no longer makes a round trip through L2 / HBM between the two.
+ * Both return -2 outside the geometry they cover (the caller then uses the older chain).                                       */
+int gptst_cap_hop_ev(const float* s, const float* dyn, float* e1, float* v, int B, int T, int D, int H, int HT, void* stream);
+int gptst_cap_recon_proj(const float* c, const float* v, const float* x, const void* wfrag, const float* bias, float* out,
+                         float* recon, int B, int T, int N, int D, int H, void* stream);
+
 /* ---- eval-path glue next to the encoder ----------------------------------------------
  * Fusion gate of Enhance_model (reference model/Model.py:12-17, called from Model.py:106-109):
  *     z = sigmoid(HS_fc(flow) + HT_fc(time)),  h = z * flow + (1 - z) * time          (then output_fc(h))

@@ -7,8 +7,8 @@ TAG=${1:-r02}
 O=gpurun_out
 mkdir -p $O
 # skip the warm-up + capture launches: profile the LAST graph replays only (4 kernels per chain)
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:"cap_route|cap_hop_e1|cap_recon_hop|gproj2_fwd|cap_fwd" \
-    --launch-skip 24 --launch-count 8 -f -o $O/prof_cap_fwd_$TAG python bench.py --cap-only > $O/ncu_cap_$TAG.log 2>&1
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:"cap_route|cap_hop_e1|cap_hop_ev|cap_recon_hop|cap_recon_proj|gproj2_fwd" \
+    --launch-skip 24 --launch-count 6 -f -o $O/prof_cap_fwd_$TAG python bench.py --cap-only > $O/ncu_cap_$TAG.log 2>&1
 ncu -i $O/prof_cap_fwd_$TAG.ncu-rep --page raw --csv > $O/ncu_cap_$TAG.csv 2>/dev/null
 python - "$O/ncu_cap_$TAG.csv" "$TAG" <<'PY'
 import csv, json, subprocess, sys
