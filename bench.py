@@ -396,7 +396,12 @@ def run_ours(args):
     run_init(model, 0)
     dp.broadcast_parameters(model)
     from gptst_b200.train import PretrainStep
-    reducer = dp.FlatGradAllReduce(model.parameters()) if world > 1 else None
+    # two buckets (decoder | encoder + scorer): rank-summed gradients stay in the flat all-reduce buffers and the fused optimiser
+    # reads them there with 1/world folded into its clip coefficient; the decoder bucket's collective overlaps the encoder backward
+    if world > 1 and not args.eager:
+        reducer = dp.BucketedGradAllReduce(dp.pretrain_buckets(model))
+    else:
+        reducer = dp.FlatGradAllReduce(model.parameters()) if world > 1 else None
     stepper = PretrainStep(model, lr=3e-3, max_grad_norm=5.0, loss="probe", use_graph=not args.eager, reducer=reducer)
 
     # synthetic inputs (standard normal); distinct per rank

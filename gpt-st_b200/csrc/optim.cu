@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(256) opt_sqnorm_kernel(const OptEntry* __restr
     }
 }
 
-// hyper = {lr, beta1, beta2, eps, max_norm (<=0: no clipping)}
+// hyper = {lr, beta1, beta2, eps, max_norm (<=0: no clipping), grad_scale}.  grad_scale multiplies every gradient before the norm
+// and the update: data-parallel training hands over the SUM of the ranks' gradients and 1/world here, so the averaging costs no
+// pass of its own (gptst_b200/dp.py BucketedGradAllReduce).
 __global__ void __launch_bounds__(256) opt_adam_kernel(const OptEntry* __restrict__ tab, const int2* __restrict__ blocks,
                                                        const float* __restrict__ partial, int nblocks, const int* __restrict__ step,
                                                        const float* __restrict__ hyper, float* __restrict__ norm_out) {
@@ -56,14 +58,14 @@ __global__ void __launch_bounds__(256) opt_adam_kernel(const OptEntry* __restric
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += red[w];
-        const float norm = sqrtf(t), max_norm = hyper[4];
+        const float norm = sqrtf(t) * hyper[5], max_norm = hyper[4];
         float c = 1.f;
         if (max_norm > 0.f) c = fminf(1.f, max_norm / (norm + 1e-6f));
         coef_s = c;
         if (blockIdx.x == 0 && norm_out) norm_out[0] = norm;
     }
     __syncthreads();
-    const float coef = coef_s, lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+    const float coef = coef_s * hyper[5], lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
     const int2 bm = blocks[blockIdx.x];
     const OptEntry e = tab[bm.x];
     const float t = (float)(*reinterpret_cast<const int*>(e.t));

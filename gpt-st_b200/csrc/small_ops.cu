@@ -762,23 +762,16 @@ __global__ void __launch_bounds__(256) sum_partials_warp_kernel(SumSegs s) {
 }  // namespace sm
 }  // namespace gptst
 
-// ins[k]: (parts[k], numel[k]) contiguous partials, outs[k]: (numel[k]); n <= 8 segments
-extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n,
-                                  void* stream) {
-    if (!ins || !outs || !numel || !parts || n <= 0) return -1;
-    if (n > 8) return -2;
+// ins[k]: (parts[k], numel[k]) contiguous partials, outs[k]: (numel[k]); n <= 8 segments.
+// Segments with few elements and many partials (the 255 per-CTA partials of a cap's dWp / dbp) take the warp-per-element
+// kernel, everything else the float4 lanes; a mixed call becomes two launches (a float4 lane walking 255 partials serially
+// is ~100 us of dependent L2 misses -- it used to be the tail of every cap backward's side stream).
+static int sum_partials_launch(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n,
+                               bool warp_path, cudaStream_t stream) {
     gptst::sm::SumSegs s;
-    bool vec = true;
-    int maxparts = 0;
-    for (int k = 0; k < n; ++k) {
-        if (!ins[k] || !outs[k] || numel[k] <= 0 || parts[k] <= 0) return -1;
+    bool vec = !warp_path;
+    for (int k = 0; k < n; ++k)
         if (numel[k] % 4 != 0 || ((uintptr_t)ins[k] & 15) != 0 || ((uintptr_t)outs[k] & 15) != 0) vec = false;
-        if (parts[k] > maxparts) maxparts = parts[k];
-    }
-    long raw = 0;
-    for (int k = 0; k < n; ++k) raw += numel[k];
-    const bool warp_path = raw <= 16384 && maxparts >= 64;
-    if (warp_path) vec = false;
     long tot = 0;
     for (int k = 0; k < 8; ++k) {
         s.start[k] = tot;
@@ -793,14 +786,33 @@ extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, c
     if (warp_path) {
         long blocks = (tot + 7) / 8;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        gptst::sm::sum_partials_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+        gptst::sm::sum_partials_warp_kernel<<<(unsigned)blocks, 256, 0, stream>>>(s);
         return (int)cudaGetLastError();
     }
     long blocks = (tot + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (vec) gptst::sm::sum_partials_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
-    else gptst::sm::sum_partials_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s);
+    if (vec) gptst::sm::sum_partials_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(s);
+    else gptst::sm::sum_partials_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(s);
     return (int)cudaGetLastError();
+}
+
+extern "C" int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n,
+                                  void* stream) {
+    if (!ins || !outs || !numel || !parts || n <= 0) return -1;
+    if (n > 8) return -2;
+    for (int k = 0; k < n; ++k)
+        if (!ins[k] || !outs[k] || numel[k] <= 0 || parts[k] <= 0) return -1;
+    const float* gi[2][8]; float* go[2][8]; long gn[2][8]; int gp[2][8]; int cnt[2] = {0, 0};
+    for (int k = 0; k < n; ++k) {
+        const int w = (numel[k] <= 16384 && parts[k] >= 64) ? 1 : 0;
+        gi[w][cnt[w]] = ins[k]; go[w][cnt[w]] = outs[k]; gn[w][cnt[w]] = numel[k]; gp[w][cnt[w]] = parts[k]; ++cnt[w];
+    }
+    for (int w = 0; w < 2; ++w) {
+        if (!cnt[w]) continue;
+        const int rc = sum_partials_launch(gi[w], go[w], gn[w], gp[w], cnt[w], w == 1, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // Backward of the score head:  dz = prob * (dprob - <prob, dprob>) ;  dh = dz W3 ;  dW3_part[cta] = dz^T h ;  db3_part[cta] = sum dz

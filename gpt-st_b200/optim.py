@@ -28,16 +28,22 @@ class FusedAdamClip:
         self.device = dev
         self.state = {}                                    # param -> (exp_avg, exp_avg_sq, int32 device step counter)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, max_grad_norm if max_grad_norm else 0.0],
+        # last entry: gradient scale (1/world when the step hands over rank-summed gradients, see step(grads=...))
+        self.hyper = torch.tensor([lr, betas[0], betas[1], eps, max_grad_norm if max_grad_norm else 0.0, 1.0],
                                   dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._tables = {}                                  # key -> [pinned table, dev table, dev block map, partial, nblocks, pinned map]
         self._captures = 0
         self.chunk = _lib.lib().gptst_opt_chunk()
         self._pre = None                                   # buffers of prefetch_tables() waiting for step()
+        self._grads = None
 
     def set_lr(self, lr: float) -> None:
         self.hyper[0:1].fill_(lr)
+
+    def set_grad_scale(self, scale: float) -> None:
+        """Every gradient is multiplied by `scale` before the norm and the update (1/world for rank-summed gradients)."""
+        self.hyper[5:6].fill_(float(scale))
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -56,7 +62,7 @@ class FusedAdamClip:
                                  torch.zeros_like(p, memory_format=torch.contiguous_format),
                                  torch.zeros(1, dtype=torch.int32, device=p.device))
             m, v, tcount = self.state[p]
-            g = p.grad
+            g = self._grad_of(p)
             if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
             n = p.numel()
@@ -121,7 +127,7 @@ class FusedAdamClip:
                                  torch.zeros_like(p, memory_format=torch.contiguous_format),
                                  torch.zeros(1, dtype=torch.int32, device=p.device))
             m, v, tcount = self.state[p]
-            g = p.grad
+            g = self._grad_of(p)
             if not (p.is_contiguous() and g.is_contiguous()) or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdamClip: fp32 contiguous parameters / gradients only")
             n = p.numel()
@@ -135,7 +141,15 @@ class FusedAdamClip:
         self._pre = None
         return [pinned, tdev, bdev, part, len(bmap), bpin, None]
 
-    def step(self) -> None:
+    def _grad_of(self, p):
+        g = self._grads.get(id(p)) if self._grads else None
+        return p.grad if g is None else g
+
+    def step(self, grads=None) -> None:
+        """grads: optional {id(param): tensor} -- gradients to read INSTEAD of ``param.grad`` (views into the flat all-reduce
+        buffers of data-parallel training, so nothing is copied back into ``.grad``); which parameters are live is still
+        decided by ``param.grad is not None``."""
+        self._grads = grads
         live = [p for p in self.params if p.grad is not None]
         pre = getattr(self, "_pre", None)
         if not live:

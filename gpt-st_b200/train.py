@@ -38,6 +38,12 @@ class PretrainStep:
         if optimizer is None and use_graph and fused_optimizer:
             from .optim import FusedAdamClip
             self.fused_opt = FusedAdamClip(self.params, lr=lr, eps=1e-8, max_grad_norm=max_grad_norm)
+        if isinstance(reducer, _dp.BucketedGradAllReduce):
+            if self.fused_opt is None:
+                raise ValueError("BucketedGradAllReduce leaves the rank-summed gradients in flat buffers: it needs the fused "
+                                 "optimiser (use FlatGradAllReduce with torch optimisers)")
+            self.fused_opt.set_grad_scale(reducer.scale)
+            reducer.arm()
         self.opt = optimizer or (None if self.fused_opt else torch.optim.Adam(self.params, lr=lr, eps=1e-8, capturable=use_graph,
                                                                               foreach=True))
         if isinstance(loss, str):
@@ -73,10 +79,11 @@ class PretrainStep:
         outs = self.model(src, src, None, epoch)
         loss = self.loss_fn(outs, src, epoch)
         loss.backward()
+        gviews = None
         if self.reducer is not None:
-            self.reducer.reduce()
+            gviews = self.reducer.reduce()             # Bucketed...: {id(param): rank-summed view}; Flat...: None (in place)
         if self.fused_opt is not None:
-            self.fused_opt.step()                      # clip + Adam, two launches
+            self.fused_opt.step(gviews or None)        # clip + Adam, two launches (1/world folded into the clip coefficient)
         else:
             if self.max_grad_norm is not None:
                 torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, foreach=True)

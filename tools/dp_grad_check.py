@@ -74,22 +74,43 @@ if rank == 0:
             print(f"gradient mismatch {k}: {err:.3e}")
     ok = ok and len({int(c.item()) for c in none_counts}) == 1
 
-# the reducer inside the captured graph: ranks must stay in lock step
-stepper = PretrainStep(model, lr=3e-3, max_grad_norm=5.0, loss="probe", use_graph=True, reducer=red)
+# the reducers inside the captured graph: ranks must stay in lock step, and the bucketed exchange (rank-summed gradients left in
+# the flat buffers, 1/world folded into the clip coefficient, decoder bucket overlapped with the encoder backward) must land on
+# the same parameters as the flat one (same draws: seeded torch / python RNG before each run)
+import copy
 xs = xg[rank::world].to(dev)
-for i in range(7):
-    stepper(xs, epoch)
-torch.cuda.synchronize()
-flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+
+
+def graph_run(m, reducer, steps=7):
+    torch.manual_seed(123 + rank)
+    random.seed(77)
+    st = PretrainStep(m, lr=3e-3, max_grad_norm=5.0, loss="probe", use_graph=True, reducer=reducer)
+    for _ in range(steps):
+        st(xs, epoch)
+    torch.cuda.synchronize()
+    return st, torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+
+
+model_b = copy.deepcopy(model)
+stepper, flat = graph_run(model, red)
+red_b = dp.BucketedGradAllReduce(dp.pretrain_buckets(model_b))
+stepper_b, flat_b = graph_run(model_b, red_b)
 ref = flat.clone()
 dist.broadcast(ref, src=0)
 sync_err = (flat - ref).abs().max()
+ref_b = flat_b.clone()
+dist.broadcast(ref_b, src=0)
+sync_err = torch.maximum(sync_err, (flat_b - ref_b).abs().max())
 dist.all_reduce(sync_err, op=dist.ReduceOp.MAX)
+bucket_vs_flat = ((flat_b - flat).abs().max() / flat.abs().max()).item()
 if rank == 0:
-    ok = ok and sync_err.item() == 0.0
+    ok = ok and sync_err.item() == 0.0 and bucket_vs_flat <= 1e-4
     print(json.dumps({"world": world, "epoch": epoch, "ok": bool(ok), "worst_rel_grad_err_vs_single_gpu": worst,
                       "params_without_grad": n_none, "all_reduce_numel": red.last_numel, "graph_replays": stepper.replays,
-                      "param_max_diff_across_ranks_after_7_graph_steps": sync_err.item()}), flush=True)
+                      "param_max_diff_across_ranks_after_7_graph_steps": sync_err.item(),
+                      "bucketed_vs_flat_param_rel_diff_after_7_graph_steps": bucket_vs_flat,
+                      "bucketed_all_reduce_numel": red_b.last_numel}), flush=True)
+stepper_b._graphs.clear()
 stepper._graphs.clear()
 import gc
 gc.collect()
