@@ -134,15 +134,38 @@ class hyperTem(nn.Module):
         self.weights_pool = _uninit(embed_dim, dim_in, dim_out)
         self.bias_pool = _uninit(embed_dim, dim_out)
 
-    def tables(self, node_embeddings, time_eb):
-        """Parameter-side contractions (independent of eb): per-node T x T mix and time-adaptive weights."""
-        A = ops.lowrank_table(node_embeddings, self.adj)                # einsum("nk,kht->nht")
-        Mn = ops.mix_matrix(A) if A.is_cuda else torch.einsum("nht,nhs->nts", A, A)   # two hops, no nonlinearity in between
+    def tables(self, node_embeddings, time_eb, aux=None):
+        """Parameter-side contractions (independent of eb): per-node T x T mix and time-adaptive weights.  aux = a second side
+        stream for the mix-matrix branch (A_n, M_n): in backward its gradient chain (dM_n -> dA_n -> d adj, dE) then runs beside
+        the weight branch (dW_bt -> d pool, d time_eb) instead of behind it."""
+        fused = (node_embeddings.is_cuda and ops.hypertem_fused_enabled(self.weights_pool.shape[-1], self.adj.shape[-1],
+                                                                        ops.default_precision()))
+        mb = {} if fused else None
+        cur = torch.cuda.current_stream() if node_embeddings.is_cuda else None
+
+        def mix_branch():
+            A = ops.lowrank_table(node_embeddings, self.adj)            # einsum("nk,kht->nht")
+            Mn = ops.mix_matrix(A) if A.is_cuda else torch.einsum("nht,nhs->nts", A, A)   # two hops, no nonlinearity in between
+            return ops.hypertem_params_m(mb, Mn) if fused else Mn
+
+        if fused and aux is not None:
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            aux.wait_event(fork)
+            with torch.cuda.stream(aux):
+                Mn = mix_branch()
+                ev_m = torch.cuda.Event()
+                ev_m.record(aux)
+            Mn.record_stream(cur)
+        else:
+            Mn, ev_m = mix_branch(), None
         W = ops.lowrank_table(time_eb, self.weights_pool)               # einsum("btd,dio->btio")
         bias = ops.lowrank_table(time_eb, self.bias_pool)
-        if Mn.is_cuda and ops.hypertem_fused_enabled(W.shape[-1], Mn.shape[-1], ops.default_precision()):
-            # fused block: the parameter-side node lives on THIS stream, so dM_n / dW_bt / db_bt are computed here in backward
-            Mn, W, bias, mb = ops.hypertem_params(Mn, W, bias)
+        if fused:
+            # fused block: the parameter-side nodes live on THESE streams, so dM_n / dW_bt / db_bt are computed here in backward
+            W, bias = ops.hypertem_params_w(mb, W, bias)
+            if ev_m is not None:
+                cur.wait_event(ev_m)       # forward join: the caller's single event covers both branches
             return Mn, W, bias, mb["wf"], mb["wb"], mb
         if Mn.is_cuda:
             # (P, N, T, T) stride-0 view: the dM_n partials of the backward are summed on this stream (ops.expand_partials)
@@ -217,7 +240,8 @@ class STHCN(nn.Module):
                 "cap": [getattr(self, f"cap{i}").tables(Es, time_eb_spg, teb) for i in (1, 2)]}
 
     def prologue_streams(self, source, pool, fork, main):
-        """`prologue` spread over nine side streams (three time embeddings, then one stream per block): inside a captured
+        """`prologue` spread over side streams (three time embeddings, then one stream per block and a second one per hyperTem
+        for its mix-matrix branch, two for the gradient accumulation of the shared node embeddings): inside a captured
         CUDA graph each stream is a linear dependency chain, and autograd replays the same streams in backward, so with
         one stream per block the table gradients of a block only wait for that block's own backward kernel instead of
         queueing behind every other block's (they used to form a 570 us serial tail after the last main kernel)."""
@@ -233,14 +257,30 @@ class STHCN(nn.Module):
             embs.append(e)
             evs.append(ev)
         time_eb, teb, time_eb_spg = embs
+        # The node embeddings are shared by the four hyperTem (two cap) blocks.  Autograd accumulates a leaf's gradient on the
+        # stream of its FIRST use -- hyperTem1's (cap1's) table stream, the block whose backward runs LAST: its parameter
+        # gradients then queue behind the additions of the other blocks' contributions, i.e. behind their whole table chains
+        # (measured: the last block's side chain started 100 us after its inputs were ready).  A view made on a dedicated
+        # stream moves the accumulation (and the leaf's AccumulateGrad node) there.
         E, Es = self.node_embeddings, self.node_embeddings_spg
+        if len(pool) >= 15:
+            for k, name in ((13, "E"), (14, "Es")):
+                pool[k].wait_event(fork)
+                with torch.cuda.stream(pool[k]):
+                    if name == "E":
+                        E = E.view_as(E)
+                    else:
+                        Es = Es.view_as(Es)
+                    evj = torch.cuda.Event()
+                    evj.record(pool[k])
+                main.wait_event(evj)                      # (no kernel ran there; a forked capture stream must be joined)
         pro = {"ht": [], "cap": [], "ht_ev": [], "cap_ev": []}
         for i in range(4):
             st = pool[3 + i]
             st.wait_event(evs[0])
             time_eb.record_stream(st)
             with torch.cuda.stream(st):
-                tb = getattr(self, f"hyperTem{i + 1}").tables(E, time_eb)
+                tb = getattr(self, f"hyperTem{i + 1}").tables(E, time_eb, pool[9 + i] if len(pool) >= 15 else None)
                 ev = torch.cuda.Event()
                 ev.record(st)
             for t in tb:
@@ -533,7 +573,8 @@ class GPTST_Model(nn.Module):
             # Autograd replays the scorer's backward (KL branch) on the same streams, where it is NOT critical but competes with
             # the head of the main backward chain: GPTST_B200_SCORER_PRIO=low is the A/B knob for that trade.
             sp = 0 if os.environ.get("GPTST_B200_SCORER_PRIO", "high") == "low" else -1
-            self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(9)], [torch.cuda.Stream(device=dev) for _ in range(9)],
+            # per STHCN: 3 time embeddings, 4 hyperTem weight branches, 2 caps, 4 hyperTem mix-matrix branches, 2 accumulation streams
+            self._streams = (key, [torch.cuda.Stream(device=dev) for _ in range(15)], [torch.cuda.Stream(device=dev) for _ in range(15)],
                              torch.cuda.Stream(device=dev, priority=sp), [torch.cuda.Stream(device=dev, priority=sp) for _ in range(2)])
         fork = torch.cuda.Event()
         fork.record(main)

@@ -35,10 +35,19 @@ def launch_count() -> int:
     return _launches
 
 
+_CAPTURE_DEBUG = os.environ.get("GPTST_B200_CAPTURE_DEBUG", "0") == "1"
+
+
 def _stream() -> int:
     global _launches
     _launches += 1
-    return torch.cuda.current_stream().cuda_stream
+    st = torch.cuda.current_stream().cuda_stream
+    if _CAPTURE_DEBUG:     # debugging aid: find the first launch after a stream capture got invalidated
+        from cuda.bindings import runtime as _rt
+        err, status = _rt.cudaStreamIsCapturing(st)
+        if int(status) == 2:
+            raise RuntimeError(f"stream capture already INVALIDATED before launch #{_launches} (err {err})")
+    return st
 
 
 def _count(n: int) -> None:
@@ -280,42 +289,57 @@ def _zero_like_shape(shape, device):
     return z.expand(tuple(shape))
 
 
-class _HyperTemParams(torch.autograd.Function):
-    """(Mn, W, bias) -> the same three tensors; the forward also packs W into the fragment-ordered fp16 tables of the fused
-    kernels (mailbox['wf'], ['wb']).  The backward ignores its incoming placeholders and computes the real dM_n, dW_bt, db_bt
-    from what the block's backward left in the mailbox."""
+class _HyperTemParamsW(torch.autograd.Function):
+    """(W, bias) -> the same two tensors; the forward also packs W into the fragment-ordered fp16 tables of the fused kernels
+    (mailbox['wf'], ['wb']).  The backward ignores its incoming placeholders: the block's backward has already launched the
+    dW_bt / db_bt kernel on THIS node's stream (as soon as dOut existed, beside the main backward kernel) and left the
+    per-split partials in the mailbox; here they are summed."""
 
     @staticmethod
-    def forward(ctx, mb, Mn, W, bias):
-        Mn, W, bias = Mn.contiguous(), W.contiguous(), bias.contiguous()
-        _chk(Mn, W, bias)
+    def forward(ctx, mb, W, bias):
+        W, bias = W.contiguous(), bias.contiguous()
+        _chk(W, bias)
         L = _lib.lib()
         G = W.shape[0] * W.shape[1]
         nbytes = L.gptst_hypertem_wfrag_bytes(G)
         wf = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
         wb = torch.empty(nbytes, dtype=torch.uint8, device=W.device)
         _lib.check(L.gptst_hypertem_pack_w(_p(W), _p(wf), _p(wb), G, _stream()), "gptst_hypertem_pack_w")
-        mb["wf"], mb["wb"], mb["stream"] = wf, wb, torch.cuda.current_stream()
+        mb["wf"], mb["wb"], mb["stream_w"] = wf, wb, torch.cuda.current_stream()
         ctx.mb = mb
-        return Mn.view_as(Mn), W.view_as(W), bias.view_as(bias)
+        return W.view_as(W), bias.view_as(bias)
 
     @staticmethod
-    def backward(ctx, _gM, _gW, _gb):
+    def backward(ctx, _gW, _gb):
         mb = ctx.mb
-        dout, mask, ret, dret, eb = (mb.pop(k) for k in ("dout", "mask", "ret", "dret", "eb"))
+        dWp, dbp = mb.pop("dWp"), mb.pop("dbp")
+        dW, db = sum_partials(dWp, dbp)
+        return None, dW, db
+
+
+class _HyperTemParamsM(torch.autograd.Function):
+    """Mn -> Mn on the stream where the mix matrices are produced; the backward computes the real dM_n there from what the
+    block's backward left in the mailbox (dret, eb), independent of the weight-side chain."""
+
+    @staticmethod
+    def forward(ctx, mb, Mn):
+        Mn = Mn.contiguous()
+        _chk(Mn)
+        mb["stream_m"] = torch.cuda.current_stream()
+        ctx.mb = mb
+        return Mn.view_as(Mn)
+
+    @staticmethod
+    def backward(ctx, _gM):
+        mb = ctx.mb
+        dret, eb = mb.pop("dret"), mb.pop("eb")
         B, T, N, D = eb.shape
         L = _lib.lib()
-        G = B * T
-        splits = L.gptst_gproj_splits(G, N, D)
-        dWp = torch.empty((splits, B, T, D, D), device=eb.device, dtype=torch.float32)
-        dbp = torch.empty((splits, B, T, D), device=eb.device, dtype=torch.float32)
-        _lib.check(L.gptst_hypertem_dw(_p(dout), _p(mask), _p(ret), _p(dWp), _p(dbp), B, T, N, D, mask.shape[1], splits, _stream()),
-                   "gptst_hypertem_dw")
         sp = L.gptst_tmix_bwd_splits(B, N)
         dMp = torch.empty((sp, N, T, T), device=eb.device, dtype=torch.float32)
         _lib.check(L.gptst_tmix_dM2(_p(dret), _p(eb), _p(dMp), B, T, N, D, sp, _stream()), "gptst_tmix_dM2")
-        dM, dW, db = sum_partials(dMp, dWp, dbp)
-        return None, dM, dW, db
+        (dM,) = sum_partials(dMp)
+        return None, dM
 
 
 class _HyperTemFused(torch.autograd.Function):
@@ -344,27 +368,57 @@ class _HyperTemFused(torch.autograd.Function):
         mb = ctx.mb
         dout = dout.contiguous()
         B, T, N, D = eb.shape
+        L = _lib.lib()
+        cur = torch.cuda.current_stream()
+        if ctx.want_params:
+            # dW_bt / db_bt only need dOut, the sign mask and ret: launch them NOW on the weight-side stream, beside the main
+            # backward kernel (they used to wait for it and formed the tail of the step behind the first block's backward)
+            side = mb["stream_w"]
+            G = B * T
+            splits = L.gptst_gproj_splits(G, N, D)
+            if side != cur:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+                for t in (dout, mask, ret):
+                    t.record_stream(side)
+            with torch.cuda.stream(side):
+                dWp = torch.empty((splits, B, T, D, D), device=eb.device, dtype=torch.float32)
+                dbp = torch.empty((splits, B, T, D), device=eb.device, dtype=torch.float32)
+                _lib.check(L.gptst_hypertem_dw(_p(dout), _p(mask), _p(ret), _p(dWp), _p(dbp), B, T, N, D, mask.shape[1], splits,
+                                               _stream()), "gptst_hypertem_dw")
+            mb.update(dWp=dWp, dbp=dbp)
         deb = torch.empty_like(eb)
         dret = torch.empty_like(eb) if ctx.want_params else None
-        _lib.check(_lib.lib().gptst_hypertem_bwd(_p(dout), _p(mask), _p(Mn), _p(wb), _p(deb), _p(dret), B, T, N, D, _stream()),
+        _lib.check(L.gptst_hypertem_bwd(_p(dout), _p(mask), _p(Mn), _p(wb), _p(deb), _p(dret), B, T, N, D, _stream()),
                    "gptst_hypertem_bwd")
         if not ctx.want_params:
             return deb, None, None, None, None
-        side = mb["stream"]
-        if side != torch.cuda.current_stream():
-            for t in (dout, mask, ret, dret, eb):
-                t.record_stream(side)
-        mb.update(dout=dout, mask=mask, ret=ret, dret=dret, eb=eb)
+        sm_ = mb["stream_m"]
+        if sm_ != cur:
+            for t in (dret, eb):
+                t.record_stream(sm_)
+        mb.update(dret=dret, eb=eb)
         sM, sW, sb = ctx.shapes
         dev = eb.device
         return deb, _zero_like_shape(sM, dev), _zero_like_shape(sW, dev), _zero_like_shape(sb, dev), None
 
 
+def hypertem_params_w(mb, W, bias):
+    """Weight-side parameter node of the fused hyperTem block (call it where W_bt / bias_bt are produced)."""
+    return _HyperTemParamsW.apply(mb, W, bias)
+
+
+def hypertem_params_m(mb, Mn):
+    """Mix-matrix-side parameter node of the fused hyperTem block (call it where M_n is produced)."""
+    return _HyperTemParamsM.apply(mb, Mn)
+
+
 def hypertem_params(Mn, W, bias):
-    """Parameter-side node of the fused hyperTem block: call it where the tables are produced (their stream is where the
-    parameter gradients will be computed).  Returns (Mn, W, bias, mailbox) for `hypertem_fused`."""
+    """Both parameter-side nodes on the current stream.  Returns (Mn, W, bias, mailbox) for `hypertem_fused`."""
     mb = {}
-    Mn2, W2, b2 = _HyperTemParams.apply(mb, Mn, W, bias)
+    Mn2 = hypertem_params_m(mb, Mn)
+    W2, b2 = hypertem_params_w(mb, W, bias)
     return Mn2, W2, b2, mb
 
 

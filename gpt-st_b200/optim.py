@@ -37,6 +37,7 @@ class FusedAdamClip:
         self.chunk = _lib.lib().gptst_opt_chunk()
         self._pre = None                                   # buffers of prefetch_tables() waiting for step()
         self._grads = None
+        self._reserved = None                              # pinned buffers allocated by reserve() for the next capture
 
     def set_lr(self, lr: float) -> None:
         self.hyper[0:1].fill_(lr)
@@ -51,6 +52,15 @@ class FusedAdamClip:
                 p.grad = None
             elif p.grad is not None:
                 p.grad.zero_()
+
+    def reserve(self) -> None:
+        """Allocate the pinned staging buffers of the NEXT captured step (call right before the capture begins).  Pinning
+        memory inside a capture makes torch's host allocator poll the events of earlier pinned blocks (cudaEventQuery), which
+        is illegal while a global-mode capture is under way and invalidates it -- depending on what earlier code left in the
+        host cache (seen as a capture failure in the middle of the GPU test suite)."""
+        nblocks = sum((p.numel() + self.chunk - 1) // self.chunk for p in self.params)
+        self._reserved = (torch.zeros((len(self.params), 6), dtype=torch.int64).pin_memory(),
+                          torch.zeros((nblocks, 2), dtype=torch.int32).pin_memory())
 
     def _table(self, live):
         """(Re)build the pointer table for the current gradient tensors.  Inside a CUDA-graph capture this runs once:
@@ -76,8 +86,13 @@ class FusedAdamClip:
         key = (tuple(id(p) for p in live), self._captures if capturing else 0)
         ent = self._tables.get(key)
         if ent is None:
-            pinned = torch.empty((len(rows), 6), dtype=torch.int64).pin_memory()
-            bpin = torch.tensor(bmap, dtype=torch.int32).pin_memory()
+            if capturing and self._reserved is not None:
+                pinned, bpin = self._reserved[0][:len(rows)], self._reserved[1][:len(bmap)]
+                bpin.copy_(torch.tensor(bmap, dtype=torch.int32))
+                self._reserved = None                               # the captured graph owns them from here on
+            else:
+                pinned = torch.empty((len(rows), 6), dtype=torch.int64).pin_memory()
+                bpin = torch.tensor(bmap, dtype=torch.int32).pin_memory()
             bdev = torch.empty((len(bmap), 2), dtype=torch.int32, device=self.device)
             bdev.copy_(bpin, non_blocking=True)                     # pinned -> device: legal inside a capture
             ent = [pinned, torch.empty((len(rows), 6), dtype=torch.int64, device=self.device), bdev,
@@ -102,8 +117,12 @@ class FusedAdamClip:
         if os.environ.get("GPTST_B200_OPT_PREFETCH", "0") != "1" or not torch.cuda.is_current_stream_capturing():
             return
         nblocks = sum((p.numel() + self.chunk - 1) // self.chunk for p in self.params)
-        pinned = torch.zeros((len(self.params), 6), dtype=torch.int64).pin_memory()
-        bpin = torch.zeros((nblocks, 2), dtype=torch.int32).pin_memory()
+        if self._reserved is not None:
+            pinned, bpin = self._reserved
+            self._reserved = None
+        else:
+            pinned = torch.zeros((len(self.params), 6), dtype=torch.int64).pin_memory()
+            bpin = torch.zeros((nblocks, 2), dtype=torch.int32).pin_memory()
         tdev = torch.empty((len(self.params), 6), dtype=torch.int64, device=self.device)
         bdev = torch.empty((nblocks, 2), dtype=torch.int32, device=self.device)
         part = torch.empty(nblocks, dtype=torch.float32, device=self.device)

@@ -14,6 +14,7 @@ callers that own their training loop.
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Callable, Optional, Union
 
@@ -102,20 +103,34 @@ class PretrainStep:
             n = src.shape[0] * src.shape[1] * src.shape[2]
             plan_dev = self.enc.mask_plan(n, epoch).to(dev)
             self.enc.plan_override = plan_dev
-        g = torch.cuda.CUDAGraph()
+        dot = os.environ.get("GPTST_B200_GRAPH_DOT")      # debugging aid: dump the captured graph (nodes + dependency edges)
+        g = torch.cuda.CUDAGraph(keep_graph=True) if dot else torch.cuda.CUDAGraph()
         self._zero_grad()
+        if self.fused_opt is not None:
+            self.fused_opt.reserve()               # pinned staging buffers: never allocate pinned memory inside the capture
         torch.cuda.synchronize()
         from . import ops as _ops
         l0 = _ops.launch_count()
         # capture on a HIGH-priority stream: the main chain's kernel nodes inherit it, while the table prologues and their
         # gradients sit on default (lowest) priority side streams and only fill the SMs the main chain leaves idle
         cap_stream = torch.cuda.Stream(device=dev, priority=-1)
+        # No cyclic garbage collection while the capture is under way: collecting an older PretrainStep (its CUDA graph and
+        # private memory pool: cudaGraphExecDestroy / cudaFree) from inside a global-mode capture invalidates it -- a
+        # timing-dependent failure seen in the middle of the GPU test suite.  (torch.cuda.graph collects once on entry.)
+        import gc
+        gc_was_on = gc.isenabled()
+        gc.disable()
         try:
             with torch.cuda.graph(g, stream=cap_stream):
                 static_loss = self._body(static_src, epoch)
         finally:
+            if gc_was_on:
+                gc.enable()
             self.enc.plan_override = None
         self.launches_per_step = _ops.launch_count() - l0   # libgptst_b200 kernels inside one replay
+        if dot:
+            g.debug_dump(f"{dot}.phase{phase}.dot")
+            g.instantiate()
         self._graphs[(phase, tuple(src.shape))] = (g, static_src, static_loss, plan_dev)
 
     def __call__(self, source: torch.Tensor, epoch: int) -> torch.Tensor:
