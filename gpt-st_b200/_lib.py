@@ -39,6 +39,8 @@ SIGNATURES = {
     "gptst_cap_route_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_cap_route2_supported": (_i, [_i, _i, _i]),
     "gptst_cap_route_bwd_dz": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_route_fwd_z": (_i, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f]),
+    "gptst_cap_route_bwd_dz_z": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f]),
     "gptst_linear_bwd_acc_splits": (_i, [_l, _i]),
     "gptst_linear_bwd_acc": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _i, _i, _f]),
     "gptst_mask_labels": (_i, [_f, _f, _f, _l, _i, _f]),

@@ -18,7 +18,11 @@ namespace r2 {
 
 using namespace hf;
 
-template <int NW, int MINB, int PREC>
+// FROMZ: the forward kernel stored Z (gptst_cap_route_fwd_z), `x` then points at Z and nothing is recomputed -- no x / Wp
+// staging, no Z product (96 of the 168 three-term MMAs per tile), 4.4 KB of shared memory instead of 70 KB.  These kernels are
+// bound by issue slots and shared-memory operand traffic, not by HBM (profiles/ncu_route_fwd_r02.md), so reading one more
+// activation is cheaper than recomputing it.
+template <int NW, int MINB, int PREC, bool FROMZ>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bp,
                          const float* __restrict__ c, const float* __restrict__ ds, const float* __restrict__ dcr,
@@ -26,9 +30,9 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
     constexpr int D = 64;
     constexpr float WSCALE = 64.f;
     extern __shared__ __align__(128) unsigned char smraw[];
-    unsigned char* Xs = smraw;                                     // [NW*16][ROWB] x rows (fp32)
-    unsigned char* Wt = Xs + (size_t)NW * 16 * ROWB;               // [64][ROWB]
-    unsigned char* dsp = Wt + (size_t)D * ROWB;                    // [16][ROWB] ds hi|lo planes (scaled), rows >= H zero
+    unsigned char* Xs = smraw;                                     // [NW*16][ROWB] x rows (fp32)          (absent with FROMZ)
+    unsigned char* Wt = Xs + (FROMZ ? 0 : (size_t)NW * 16 * ROWB); // [64][ROWB]                           (absent with FROMZ)
+    unsigned char* dsp = Wt + (FROMZ ? 0 : (size_t)D * ROWB);      // [16][ROWB] ds hi|lo planes (scaled), rows >= H zero
     float* bps = reinterpret_cast<float*>(dsp + 16 * ROWB);        // [64]
     float* wmax = bps + D;                                         // [NW]
 
@@ -37,14 +41,26 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
     const int g = lane >> 2, t = lane & 3;
     const int slab = blockIdx.x;
     const float* xs = x + (size_t)slab * N * D;
-    for (int i = tid; i < NW * 16 * 16; i += NT) {
-        const int r = i >> 4, ch = i & 15;
-        unsigned char* dst = Xs + (size_t)r * ROWB + ch * 16;
-        if (r < N) cp_async16(dst, xs + (size_t)r * D + ch * 4);
-        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float z[8][4];
+    if (FROMZ) {
+        // Z rows straight into the accumulator-fragment layout: 8-byte loads, 8 rows x 32 B per warp request (full sectors)
+        const int ra_ = warp * 16 + g, rb_ = ra_ + 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 a = (ra_ < N) ? *reinterpret_cast<const float2*>(xs + (size_t)ra_ * D + 8 * j + 2 * t) : make_float2(0.f, 0.f);
+            const float2 b = (rb_ < N) ? *reinterpret_cast<const float2*>(xs + (size_t)rb_ * D + 8 * j + 2 * t) : make_float2(0.f, 0.f);
+            z[j][0] = a.x; z[j][1] = a.y; z[j][2] = b.x; z[j][3] = b.y;
+        }
+    } else {
+        for (int i = tid; i < NW * 16 * 16; i += NT) {
+            const int r = i >> 4, ch = i & 15;
+            unsigned char* dst = Xs + (size_t)r * ROWB + ch * 16;
+            if (r < N) cp_async16(dst, xs + (size_t)r * D + ch * 4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        stage_w_perm<PREC, NT>(Wt, Wp, WSCALE, tid);
+        for (int i = tid; i < D; i += NT) bps[i] = bp[i];
     }
-    stage_w_perm<PREC, NT>(Wt, Wp, WSCALE, tid);
-    for (int i = tid; i < D; i += NT) bps[i] = bp[i];
     // ds: each thread keeps (at most two) float2 of the H x 64 block, the slab max goes through wmax
     constexpr int DSP = (16 * 32 + NT - 1) / NT;      // float2 items per thread (rows padded to 16)
     float2 dsv[DSP];
@@ -97,17 +113,18 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
         }
     }
     // ---- Z (registers), row norms
-    float z[8][4];
-    warp_xw_tile<PREC>(z, Xs, Wt, n0, lane);
+    if (!FROMZ) warp_xw_tile<PREC>(z, Xs, Wt, n0, lane);
     const int ra = n0 + g, rb = ra + 8;
     float q0 = 0.f, q1 = 0.f;
     {
         constexpr float inv_scale = 1.f / WSCALE;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float b0 = bps[8 * j + 2 * t], b1 = bps[8 * j + 2 * t + 1];
-            z[j][0] = fmaf(z[j][0], inv_scale, b0); z[j][1] = fmaf(z[j][1], inv_scale, b1);
-            z[j][2] = fmaf(z[j][2], inv_scale, b0); z[j][3] = fmaf(z[j][3], inv_scale, b1);
+            if (!FROMZ) {
+                const float b0 = bps[8 * j + 2 * t], b1 = bps[8 * j + 2 * t + 1];
+                z[j][0] = fmaf(z[j][0], inv_scale, b0); z[j][1] = fmaf(z[j][1], inv_scale, b1);
+                z[j][2] = fmaf(z[j][2], inv_scale, b0); z[j][3] = fmaf(z[j][3], inv_scale, b1);
+            }
             q0 += z[j][0] * z[j][0] + z[j][1] * z[j][1];
             q1 += z[j][2] * z[j][2] + z[j][3] * z[j][3];
         }
@@ -230,11 +247,11 @@ cap_route2_bwd_dz_kernel(const float* __restrict__ x, const float* __restrict__ 
     }
 }
 
-template <int NW, int MINB, int PREC>
+template <int NW, int MINB, int PREC, bool FROMZ = false>
 static cudaError_t launch_bwd_dz(const float* x, const float* Wp, const float* bp, const float* c, const float* ds,
                                  const float* dcr, float* dZ, float* ddadj, int BT, int N, int H, cudaStream_t st) {
-    const size_t smem = (size_t)NW * 16 * ROWB + 64 * ROWB + 16 * ROWB + (64 + NW) * 4;
-    auto kern = cap_route2_bwd_dz_kernel<NW, MINB, PREC>;
+    const size_t smem = (FROMZ ? 0 : (size_t)NW * 16 * ROWB + 64 * ROWB) + 16 * ROWB + (64 + NW) * 4;
+    auto kern = cap_route2_bwd_dz_kernel<NW, MINB, PREC, FROMZ>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<BT, NW * 32, smem, st>>>(x, Wp, bp, c, ds, dcr, dZ, ddadj, N, H);
@@ -249,6 +266,16 @@ static cudaError_t dispatch_bwd_dz(const float* x, const float* Wp, const float*
     if (N <= 176) return launch_bwd_dz<11, 2, PREC>(x, Wp, bp, c, ds, dcr, dZ, ddadj, BT, N, H, st);
     if (N <= 208) return launch_bwd_dz<13, 2, PREC>(x, Wp, bp, c, ds, dcr, dZ, ddadj, BT, N, H, st);
     return launch_bwd_dz<16, 1, PREC>(x, Wp, bp, c, ds, dcr, dZ, ddadj, BT, N, H, st);
+}
+
+template <int PREC>
+static cudaError_t dispatch_bwd_dz_z(const float* z, const float* c, const float* ds, const float* dcr, float* dZ, float* ddadj,
+                                     int BT, int N, int H, cudaStream_t st) {
+    if (N <= 64) return launch_bwd_dz<4, 4, PREC, true>(z, nullptr, nullptr, c, ds, dcr, dZ, ddadj, BT, N, H, st);
+    if (N <= 128) return launch_bwd_dz<8, 3, PREC, true>(z, nullptr, nullptr, c, ds, dcr, dZ, ddadj, BT, N, H, st);
+    if (N <= 176) return launch_bwd_dz<11, 2, PREC, true>(z, nullptr, nullptr, c, ds, dcr, dZ, ddadj, BT, N, H, st);
+    if (N <= 208) return launch_bwd_dz<13, 2, PREC, true>(z, nullptr, nullptr, c, ds, dcr, dZ, ddadj, BT, N, H, st);
+    return launch_bwd_dz<16, 1, PREC, true>(z, nullptr, nullptr, c, ds, dcr, dZ, ddadj, BT, N, H, st);
 }
 
 }  // namespace r2
@@ -269,4 +296,14 @@ extern "C" int gptst_cap_route_bwd_dz(const float* x, const float* Wp, const flo
     cudaStream_t st = (cudaStream_t)stream;
     if (prec == 3) return (int)r2::dispatch_bwd_dz<PREC_3XTF32>(x, Wp, bp, c, ds, dcr, dZ, ddadj, B * T, N, H, st);
     return (int)r2::dispatch_bwd_dz<PREC_TF32>(x, Wp, bp, c, ds, dcr, dZ, ddadj, B * T, N, H, st);
+}
+
+// Same, from the Z the forward stored (gptst_cap_route_fwd_z): z (B,T,N,D) = x Wp^T + bp.
+extern "C" int gptst_cap_route_bwd_dz_z(const float* z, const float* c, const float* ds, const float* dcr, float* dZ,
+                                        float* ddadj, int B, int T, int N, int D, int H, int prec, void* stream) {
+    if (!z || !c || !ds || !dcr || !dZ || !ddadj || B <= 0 || T <= 0 || N <= 0) return -1;
+    if (!route2_supported(N, D, H) || (prec != 1 && prec != 3)) return -2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prec == 3) return (int)r2::dispatch_bwd_dz_z<PREC_3XTF32>(z, c, ds, dcr, dZ, ddadj, B * T, N, H, st);
+    return (int)r2::dispatch_bwd_dz_z<PREC_TF32>(z, c, ds, dcr, dZ, ddadj, B * T, N, H, st);
 }

@@ -177,8 +177,8 @@ __device__ __forceinline__ void warp_aggregate_tiles(const float (&c)[TPW][8], i
 template <int NW, int TPW, int MINB, int PREC>
 __global__ void __launch_bounds__(NW * 32, MINB)
 cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bp,
-                      const float* __restrict__ dadj, float* __restrict__ c_out, float* __restrict__ s_out, int N, int H,
-                      int R, int ntiles) {
+                      const float* __restrict__ dadj, float* __restrict__ c_out, float* __restrict__ s_out,
+                      float* __restrict__ z_out, int N, int H, int R, int ntiles) {
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned char* Prow = smraw;                                  // [ntiles*16][ROWB]
     unsigned char* Wt = Prow + (size_t)ntiles * 16 * ROWB;        // [64][ROWB]  (out o, permuted k), dead after Z
@@ -250,6 +250,14 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
             q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
             q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
             const float f0 = (ra < N) ? squash_f(q0) : 0.f, f1 = (rb < N) ? squash_f(q1) : 0.f;
+            if (z_out) {                                        // training: the backward reads Z instead of recomputing it
+                float* zo = z_out + (size_t)slab * N * D;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (ra < N) *reinterpret_cast<float2*>(zo + (size_t)ra * D + 8 * j + 2 * t) = make_float2(acc[j][0], acc[j][1]);
+                    if (rb < N) *reinterpret_cast<float2*>(zo + (size_t)rb * D + 8 * j + 2 * t) = make_float2(acc[j][2], acc[j][3]);
+                }
+            }
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -367,28 +375,28 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
 }
 
 template <int NW, int TPW, int MINB, int PREC>
-static cudaError_t launch(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int BT,
-                          int N, int H, int R, cudaStream_t st) {
+static cudaError_t launch(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, float* z,
+                          int BT, int N, int H, int R, cudaStream_t st) {
     const int ntiles = (N + 15) / 16;
     const size_t smem = smem_bytes(NW, ntiles, H);
     auto kern = cap_route2_fwd_kernel<NW, TPW, MINB, PREC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<BT, NW * 32, smem, st>>>(x, Wp, bp, dadj, c, s, N, H, R, ntiles);
+    kern<<<BT, NW * 32, smem, st>>>(x, Wp, bp, dadj, c, s, z, N, H, R, ntiles);
     return cudaGetLastError();
 }
 
 template <int PREC>
-static cudaError_t dispatch(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int BT,
-                            int N, int H, int R, cudaStream_t st) {
+static cudaError_t dispatch(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, float* z,
+                            int BT, int N, int H, int R, cudaStream_t st) {
     // One tile per warp.  Two tiles per warp (6 warps, 74 KB -> three slabs per SM) were measured on the B200 and lost:
     // 13 % fewer shared-memory wavefronts but 25 % instead of 31 % active warps -> 54.9 vs 50.4 us
     // (profiles/ncu_route_fwd_r02.md); the kernel template keeps TPW as a parameter, only TPW = 1 is instantiated.
-    if (N <= 64) return launch<4, 1, 4, PREC>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
-    if (N <= 128) return launch<8, 1, 3, PREC>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
-    if (N <= 176) return launch<11, 1, 2, PREC>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
-    if (N <= 208) return launch<13, 1, 2, PREC>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
-    return launch<16, 1, 1, PREC>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
+    if (N <= 64) return launch<4, 1, 4, PREC>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
+    if (N <= 128) return launch<8, 1, 3, PREC>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
+    if (N <= 176) return launch<11, 1, 2, PREC>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
+    if (N <= 208) return launch<13, 1, 2, PREC>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
+    return launch<16, 1, 1, PREC>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
 }
 
 }  // namespace r2
@@ -403,10 +411,10 @@ bool route2_supported(int N, int D, int H) {
     return !legacy && D == 64 && N <= 256 && H >= 1 && H <= 15;
 }
 
-cudaError_t route2_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int BT,
+cudaError_t route2_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, float* z, int BT,
                        int N, int H, int R, int prec, cudaStream_t st) {
-    if (prec == PREC_3XTF32) return r2::dispatch<PREC_3XTF32>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
-    return r2::dispatch<PREC_TF32>(x, Wp, bp, dadj, c, s, BT, N, H, R, st);
+    if (prec == PREC_3XTF32) return r2::dispatch<PREC_3XTF32>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
+    return r2::dispatch<PREC_TF32>(x, Wp, bp, dadj, c, s, z, BT, N, H, R, st);
 }
 
 }  // namespace gptst

@@ -345,7 +345,7 @@ static cudaError_t launch_route_fwd(const float* x, const float* Wp, const float
 
 // second generation (cap_route2_fwd.cu): D = 64, N <= 256, fp16-split tensor-core routing
 bool route2_supported(int N, int D, int H);
-cudaError_t route2_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, int BT,
+cudaError_t route2_fwd(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, float* z, int BT,
                        int N, int H, int R, int prec, cudaStream_t st);
 
 }  // namespace gptst
@@ -357,10 +357,19 @@ extern "C" int gptst_cap_route_fwd(const float* x, const float* Wp, const float*
     if (!x || !Wp || !bp || !dadj || !c || !s || B <= 0 || T <= 0 || N <= 0 || R < 0) return -1;
     if (H < 1 || H > 15) return -2;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((prec == 1 || prec == 3) && route2_supported(N, D, H)) return (int)route2_fwd(x, Wp, bp, dadj, c, s, B * T, N, H, R, prec, st);
+    if ((prec == 1 || prec == 3) && route2_supported(N, D, H)) return (int)route2_fwd(x, Wp, bp, dadj, c, s, nullptr, B * T, N, H, R, prec, st);
     if (D == 64 && prec == 1) return (int)launch_route_fwd<64, 1>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     if (D == 64 && prec == 3) return (int)launch_route_fwd<64, 3>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     if (D == 128 && prec == 1) return (int)launch_route_fwd<128, 1>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     if (D == 128 && prec == 3) return (int)launch_route_fwd<128, 3>(x, Wp, bp, dadj, c, s, B * T, N, H, R, st);
     return -2;
+}
+
+// Training flavour of the second-generation routing: additionally stores Z = x Wp^T + bp (B,T,N,D) for gptst_cap_route_bwd_dz_z.
+// Only where gptst_cap_route2_supported(N, D, H); returns -2 otherwise (callers then use the recomputing pair).
+extern "C" int gptst_cap_route_fwd_z(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s,
+                                     float* z, int B, int T, int N, int D, int H, int R, int prec, void* stream) {
+    if (!x || !Wp || !bp || !dadj || !c || !s || !z || B <= 0 || T <= 0 || N <= 0 || R < 0) return -1;
+    if (!((prec == 1 || prec == 3) && route2_supported(N, D, H))) return -2;
+    return (int)route2_fwd(x, Wp, bp, dadj, c, s, z, B * T, N, H, R, prec, (cudaStream_t)stream);
 }

@@ -475,11 +475,19 @@ class _CapCore(torch.autograd.Function):
         _count(2)  # route_fwd + hop_e1 + recon_hop share `st`
         c = torch.empty((B, T, H, N), device=x.device, dtype=torch.float32)
         s = torch.empty((B, T, H, D), device=x.device, dtype=torch.float32)
-        _lib.check(L.gptst_cap_route_fwd(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), B, T, N, D, H, int(num_route),
-                                         prec, st), "gptst_cap_route_fwd")
+        need_grad = any(ctx.needs_input_grad[:7])
+        # training on the second-generation kernels: the routing forward also stores Z = x Wp^T + bp, the backward reads it instead
+        # of recomputing it (these kernels are issue / shared-memory bound, not HBM bound: one more activation is the cheaper side)
+        zst = None
+        if need_grad and L.gptst_cap_route2_supported(N, D, H) and os.environ.get("GPTST_B200_CAP_Z", "store") == "store":
+            zst = torch.empty_like(x)
+            _lib.check(L.gptst_cap_route_fwd_z(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), _p(zst), B, T, N, D, H, int(num_route),
+                                               prec, st), "gptst_cap_route_fwd_z")
+        else:
+            _lib.check(L.gptst_cap_route_fwd(_p(x), _p(Wp), _p(bp), _p(dadj), _p(c), _p(s), B, T, N, D, H, int(num_route),
+                                             prec, st), "gptst_cap_route_fwd")
         v = torch.empty_like(s)
         e1 = torch.empty((B, HT, D), device=x.device, dtype=torch.float32)
-        need_grad = any(ctx.needs_input_grad[:7])
         if cap_fused_enabled(N, D, H, T, prec):
             # round 2: the hop in one launch, then reconstruction + node-adaptive projection + residual in one launch; `recon`
             # is only written because the backward reads it (never in inference)
@@ -504,14 +512,15 @@ class _CapCore(torch.autograd.Function):
                            "gptst_cap_recon_hop")
             out = gproj_fwd(recon, Wn, bn, x, node_grouped=True, act=True, prec=prec)
         if need_grad:
-            ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1)
+            ctx.save_for_backward(x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1, *([zst] if zst is not None else []))
         ctx.prec = prec
         ctx.mark_non_differentiable(c)
         return out, c
 
     @staticmethod
     def backward(ctx, dout, _dc):
-        x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1 = ctx.saved_tensors
+        x, Wp, bp, dyn, Wn, c, s, v, recon, out, e1 = ctx.saved_tensors[:11]
+        zst = ctx.saved_tensors[11] if len(ctx.saved_tensors) > 11 else None
         B, T, N, D = x.shape
         H, HT = c.shape[2], dyn.shape[1]
         L = _lib.lib()
@@ -540,8 +549,12 @@ class _CapCore(torch.autograd.Function):
         if L.gptst_cap_route2_supported(N, D, H):
             # second generation: dZ per slab, then the shared-weight contractions as one linear-layer backward
             dZ = torch.empty_like(x)
-            _lib.check(L.gptst_cap_route_bwd_dz(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dZ), _p(ddadj), B, T, N, D, H,
-                                                ctx.prec, st), "gptst_cap_route_bwd_dz")
+            if zst is not None:
+                _lib.check(L.gptst_cap_route_bwd_dz_z(_p(zst), _p(c), _p(ds), _p(dcr), _p(dZ), _p(ddadj), B, T, N, D, H, ctx.prec, st),
+                           "gptst_cap_route_bwd_dz_z")
+            else:
+                _lib.check(L.gptst_cap_route_bwd_dz(_p(x), _p(Wp), _p(bp), _p(c), _p(ds), _p(dcr), _p(dZ), _p(ddadj), B, T, N, D, H,
+                                                    ctx.prec, st), "gptst_cap_route_bwd_dz")
             rows = B * T * N
             parts = L.gptst_linear_bwd_acc_splits(rows, D)
             dWp_part = torch.empty((parts, D, D), device=x.device, dtype=torch.float32)

@@ -133,6 +133,13 @@ int gptst_cap_route2_supported(int N, int D, int H);
 int gptst_cap_route_bwd_dz(const float* x, const float* Wp, const float* bp, const float* c, const float* ds,
                            const float* dcr, float* dZ, float* ddadj, int B, int T, int N, int D, int H, int prec,
                            void* stream);
+/* Training pair that trades one activation for the recompute (reference GPTST.py:102-103 forward, SURVEY.md appendix A backward):
+ * route_fwd_z = gptst_cap_route_fwd that also stores Z = x Wp^T + bp (B,T,N,D); route_bwd_dz_z = route_bwd_dz reading that Z
+ * (no x / Wp staging, no Z product).  Same supported geometries as gptst_cap_route2_supported.                              */
+int gptst_cap_route_fwd_z(const float* x, const float* Wp, const float* bp, const float* dadj, float* c, float* s, float* z,
+                          int B, int T, int N, int D, int H, int R, int prec, void* stream);
+int gptst_cap_route_bwd_dz_z(const float* z, const float* c, const float* ds, const float* dcr, float* dZ, float* ddadj,
+                             int B, int T, int N, int D, int H, int prec, void* stream);
 int gptst_linear_bwd_acc_splits(long rows, int D);
 int gptst_linear_bwd_acc(const float* dY, const float* X, const float* W, float* dX_io, float* dW_part, float* db_part,
                          long rows, int D, int prec, int splits, void* stream);

@@ -36,6 +36,8 @@ typedef int (*cap_dv_dcr_hoprows_t)(cf, cf, cf, cf, cf, cf, float*, float*, floa
 typedef int (*cap_hop_bwd_parts_t)(int);
 typedef int (*cap_hop_bwd_cols_t)(cf, cf, cf, cf, cf, float*, float*, int, int, int, int, int, void*);
 typedef int (*cap_route_bwd_dz_t)(cf, cf, cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, void*);
+typedef int (*cap_route_fwd_z_t)(cf, cf, cf, cf, float*, float*, float*, int, int, int, int, int, int, int, void*);
+typedef int (*cap_route_bwd_dz_z_t)(cf, cf, cf, cf, float*, float*, int, int, int, int, int, int, void*);
 typedef int (*linear_bwd_acc_splits_t)(long, int);
 typedef int (*linear_bwd_acc_t)(cf, cf, cf, float*, float*, float*, long, int, int, int, void*);
 typedef int (*proj_out_fwd_t)(cf, cf, cf, float*, long, int, int, void*);
@@ -88,6 +90,7 @@ int main(int argc, char** argv) {
     if (!L) { printf("dlopen failed: %s\n", dlerror()); return 1; }
     SYM(gproj_fwd) SYM(gproj_splits) SYM(gproj_bwd) SYM(gproj3_bwd) SYM(tmix) SYM(tmix_bwd_splits) SYM(tmix_bwd)
     SYM(cap_route_fwd) SYM(cap_hop_e1) SYM(cap_recon_hop) SYM(cap_dv_dcr_hoprows) SYM(cap_hop_bwd_parts) SYM(cap_hop_bwd_cols)
+    SYM(cap_route_fwd_z) SYM(cap_route_bwd_dz_z)
     SYM(cap_route_bwd_dz) SYM(linear_bwd_acc_splits) SYM(linear_bwd_acc) SYM(proj_out_fwd) SYM(proj_out_bwd_parts) SYM(proj_out_bwd)
     SYM(score_head_fwd)
     SYM(hypertem_wfrag_bytes) SYM(hypertem_pack_w) SYM(hypertem_fwd) SYM(hypertem_bwd) SYM(hypertem_dw) SYM(tmix_dM2)
@@ -151,6 +154,8 @@ int main(int argc, char** argv) {
     bench("gproj node-grouped         bwd", 5 * Ab, iters, [&](int i) { return gproj_bwd(st[i].dout, st[i].out_n, st[i].recon, Wn, st[i].drecon, dWnp, dbnp, st[i].dx, N, B * T, gsN, rsN, D, 1, prec, sp_n, 0); });
     bench("cap_dv_dcr_hoprows         bwd", Ab + 2 * Cb, iters, [&](int i) { return cap_dv_dcr_hoprows(st[i].c, st[i].v, st[i].drecon, st[i].s, dyn, st[i].e1, st[i].dcr, st[i].dr, st[i].dp2, B, T, N, D, H, HT, 0); });
     bench("cap_hop_bwd_cols           bwd", 0.3 * Ab, iters, [&](int i) { return cap_hop_bwd_cols(st[i].s, dyn, st[i].e1, st[i].dr, st[i].dp2, st[i].ds, ddynp, B, T, D, H, HT, 0); });
+    bench("cap_route_fwd_z (+Z store) fwd", 2 * Ab + 2 * Cb, iters, [&](int i) { return cap_route_fwd_z(st[i].x, Wp, bp, dadj, st[i].c, st[i].s, st[i].dZ, B, T, N, D, H, RT, prec, 0); });
+    bench("cap_route_bwd_dz_z (from Z) bwd", 2 * Ab + 3 * Cb, iters, [&](int i) { return cap_route_bwd_dz_z(st[i].x, st[i].c, st[i].ds, st[i].dcr, st[i].dZ, st[i].ddadj, B, T, N, D, H, prec, 0); });
     bench("cap_route_bwd_dz           bwd", 2 * Ab + 3 * Cb, iters, [&](int i) { return cap_route_bwd_dz(st[i].x, Wp, bp, st[i].c, st[i].ds, st[i].dcr, st[i].dZ, st[i].ddadj, B, T, N, D, H, prec, 0); });
     bench("linear_bwd_acc (ln_p)      bwd", 4 * Ab, iters, [&](int i) { return linear_bwd_acc(st[i].dZ, st[i].x, Wp, st[i].dx, dWpp, dbpp, (long)M, D, prec, sp_l, 0); });
     bench("gproj3 shared weight       bwd (sign-mask kernel)", 4 * Ab, iters, [&](int i) { return gproj3_bwd(st[i].dZ, 0, st[i].x, Wp, st[i].dx, dWpp, dbpp, 0, 1, (int)M, 0L, (long)D, D, 0, prec, sp_l, 3, 0); });
