@@ -423,12 +423,28 @@ def run_ours(args):
             torch.cuda.profiler.start()     # `ncu --profile-from-start off` then profiles exactly the timed graph replays
         e0.record()
         last = None
-        for i in range(nsteps):
-            if e2e:
-                # public API with HOST buffers: H2D of this step's batch from pinned memory, D2H read of the loss
-                last = float(stepper(host[i % nbuf], epoch))
-            else:
-                last = stepper(resident[i % nbuf], epoch)
+        if e2e and not args.eager:
+            # public API with HOST buffers, software-pipelined the way a training loop logs: the H2D copy of batch i+1 is
+            # announced with `prefetch=` and runs under step i, and the loss of step i is read back (D2H into pinned memory,
+            # then float()) while step i+1 is already queued -- every step's input copy and loss read stay inside the timed region
+            loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            evs = [torch.cuda.Event(), torch.cuda.Event()]
+            for i in range(nsteps):
+                dl = stepper(host[i % nbuf], epoch, prefetch=host[(i + 1) % nbuf])
+                loss_host[i % 2].copy_(dl, non_blocking=True)
+                evs[i % 2].record()
+                if i > 0:
+                    evs[(i - 1) % 2].synchronize()
+                    last = float(loss_host[(i - 1) % 2])
+            evs[(nsteps - 1) % 2].synchronize()
+            last = float(loss_host[(nsteps - 1) % 2])
+        else:
+            for i in range(nsteps):
+                if e2e:
+                    # eager mode: H2D of this step's batch from pinned memory, D2H read of the loss
+                    last = float(stepper(host[i % nbuf], epoch))
+                else:
+                    last = stepper(resident[i % nbuf], epoch)
         e1.record()
         torch.cuda.synchronize()
         if args.profiler_range and not e2e:

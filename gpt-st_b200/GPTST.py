@@ -408,7 +408,7 @@ class Hypergraph_encoder(nn.Module):
         random.shuffle(order)
         return torch.tensor(order + [ada_num, rnd_num], dtype=torch.int64)
 
-    def _adaptive_mask(self, source, prob, epoch):
+    def _adaptive_mask(self, source, prob, epoch, draws=None):
         """Phase-2 mask (ref :344-413): whole classes in a shuffled order until the adaptive budget is reached, the
         last class sub-sampled, then an exact-count random fill.  Restated without host synchronisation: the class
         selection loop of the reference (one `torch.sum(...)` D2H per class) becomes a 10-element prefix sum on the
@@ -425,6 +425,8 @@ class Hypergraph_encoder(nn.Module):
         # the same two draws, in the same order, as the reference (:389, :400)
         if self.draws_override is not None:
             u1, u2 = self.draws_override["u1"], self.draws_override["u2"]
+        elif draws is not None:
+            u1, u2 = draws
         else:
             u1 = torch.rand_like(source[..., 0:1].reshape(-1))
             u2 = torch.rand_like(source[..., 0:1].reshape(-1))
@@ -501,15 +503,26 @@ class Hypergraph_encoder(nn.Module):
             else:
                 prob = score[0]                                   # joined by the caller before the loss
         else:
+            draws = None
+            if score is not None and self.draws_override is None and source.is_cuda:
+                # the two uniform draws of the mask (ref :389, :400) do not depend on the scores: issue them BEFORE joining the
+                # scorer stream, so they run beside it instead of between the score head and the mask kernels (same order, same
+                # generator state as the reference)
+                draws = (torch.rand_like(source[..., 0:1].reshape(-1)), torch.rand_like(source[..., 0:1].reshape(-1)))
             if score is None:
                 prob = self._scores(source)
             else:
                 torch.cuda.current_stream().wait_event(score[1])
                 prob = score[0]
-            final_mask = self._adaptive_mask(source, prob, epoch)
+            final_mask = self._adaptive_mask(source, prob, epoch, draws)
         final_mask = final_mask.detach()
-        masked = torch.where(final_mask == 0, torch.full_like(flow, float(self.scaler_zeros)), final_mask * flow)
-        x_in = _affine(self.dim_in_flow, masked)
+        if (i0 == 1 and source.is_cuda and source.dtype == torch.float32 and source.is_contiguous()
+                and final_mask.dtype == torch.int64 and final_mask.is_contiguous()):
+            # where(mask == 0, scaler_zeros, mask * flow) + dim_in_flow in one launch (ref :419-421)
+            x_in = ops.masked_affine1(source, final_mask, self.dim_in_flow.weight, self.dim_in_flow.bias, float(self.scaler_zeros))
+        else:
+            masked = torch.where(final_mask == 0, torch.full_like(flow, float(self.scaler_zeros)), final_mask * flow)
+            x_in = _affine(self.dim_in_flow, masked)
         enc, HS1, _ = self.STHCN_encode(source, x_in, pro)
         return enc, final_mask[..., :i0], prob, HS1.squeeze(-1).transpose(-1, -2)
 

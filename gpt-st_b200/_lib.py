@@ -63,6 +63,7 @@ SIGNATURES = {
     "gptst_score_head_bwd": (_i, [_f, _f, _f, _f, _f, _f, _l, _i, _i, _f]),
     "gptst_sum_partials": (_i, [_f, _f, _f, _f, _i, _f]),
     "gptst_affine1_fwd": (_i, [_f, _f, _f, _f, _l, _i, _f]),
+    "gptst_masked_affine1_fwd": (_i, [_f, _l, _f, C.c_float, _f, _f, _f, _f, _l, _i, _f]),
     "gptst_affine1_bwd_parts": (_i, [_l]),
     "gptst_affine1_bwd": (_i, [_f, _f, _f, _l, _i, _i, _f]),
     "gptst_gproj3_bwd": (_i, [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _l, _l, _i, _i, _i, _i, _i, _f]),

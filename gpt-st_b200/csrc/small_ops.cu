@@ -690,6 +690,43 @@ extern "C" int gptst_affine1_fwd(const float* x, const float* w, const float* b,
     return (int)cudaGetLastError();
 }
 
+// Masked input embedding of the encoder (reference GPTST.py:419-421): xm[i] = mask[i] == 0 ? fill : mask[i] * flow[i];
+// y[i][:] = xm[i] * w[:] + b[:].  One launch instead of four elementwise library kernels in front of the affine one; xm is kept
+// for the backward (dw = sum_i dy[i,:] xm[i]).
+namespace gptst {
+namespace sm {
+__global__ void __launch_bounds__(256) masked_affine1_fwd_kernel(const float* __restrict__ flow, long flow_stride,
+                                                                 const long long* __restrict__ mask, float fill,
+                                                                 const float* __restrict__ w, const float* __restrict__ b,
+                                                                 float* __restrict__ xm, float* __restrict__ y, long n, int D) {
+    const int q4 = D / 4;
+    const long total = n * q4;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+        const long r = i / q4;
+        const int q = (int)(i % q4);
+        const long long m = mask[r];
+        const float xv = (m == 0) ? fill : (float)m * flow[r * flow_stride];
+        if (q == 0) xm[r] = xv;
+        const float4 wv = *reinterpret_cast<const float4*>(w + 4 * q), bv = *reinterpret_cast<const float4*>(b + 4 * q);
+        *reinterpret_cast<float4*>(y + r * D + 4 * q) =
+            make_float4(fmaf(xv, wv.x, bv.x), fmaf(xv, wv.y, bv.y), fmaf(xv, wv.z, bv.z), fmaf(xv, wv.w, bv.w));
+    }
+}
+}  // namespace sm
+}  // namespace gptst
+
+// flow: element r at flow[r * flow_stride] (the flow channel of `source` read in place); mask (n,) int64; xm (n,), y (n, D)
+extern "C" int gptst_masked_affine1_fwd(const float* flow, long flow_stride, const long long* mask, float fill, const float* w,
+                                        const float* b, float* xm, float* y, long n, int D, void* stream) {
+    if (!flow || !mask || !w || !b || !xm || !y || n <= 0 || flow_stride <= 0) return -1;
+    if (D < 4 || D % 4 != 0) return -2;
+    long blocks = (n * (D / 4) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    gptst::sm::masked_affine1_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(flow, flow_stride, mask, fill, w, b, xm,
+                                                                                            y, n, D);
+    return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Sum of per-CTA / per-split gradient partials for up to 8 tensors in ONE launch:  out_s[i] = sum_p in_s[p * numel_s + i]
 // (fixed order -> deterministic).  A cap backward ends with five such reductions (dW_n, db_n, ddyn, dWp, dbp); as separate

@@ -839,6 +839,46 @@ def affine1(x, weight, bias):
     return _Affine1.apply(x, weight, bias)
 
 
+class _MaskedAffine1(torch.autograd.Function):
+    """Encoder input embedding (reference GPTST.py:419-421): y = dim_in_flow(where(mask == 0, fill, mask * flow)) for ONE flow
+    channel, in one launch; `flow` is read in place from `source` (element stride = source.shape[-1]).  No gradient reaches the
+    data; dw / db come from the stored masked input through the affine backward kernel."""
+
+    @staticmethod
+    def forward(ctx, source, mask, weight, bias, fill):
+        w, b = weight.contiguous().view(-1), bias.contiguous()
+        _chk(source, w, b)
+        if mask.dtype != torch.int64 or not mask.is_contiguous() or mask.numel() * source.shape[-1] != source.numel():
+            raise RuntimeError("masked_affine1: mask must be a contiguous int64 tensor with one entry per (b, t, n) cell")
+        D = w.numel()
+        n = mask.numel()
+        xm = torch.empty(n, device=source.device, dtype=torch.float32)
+        y = torch.empty(tuple(source.shape[:-1]) + (D,), device=source.device, dtype=torch.float32)
+        _lib.check(_lib.lib().gptst_masked_affine1_fwd(_p(source), source.shape[-1], _p(mask), float(fill), _p(w), _p(b), _p(xm),
+                                                       _p(y), n, D, _stream()), "gptst_masked_affine1_fwd")
+        ctx.save_for_backward(xm, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xm, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        _chk(dy)
+        D = dy.shape[-1]
+        n = dy.numel() // D
+        L = _lib.lib()
+        parts = L.gptst_affine1_bwd_parts(n)
+        part = torch.empty((parts, 2, D), device=dy.device, dtype=torch.float32)
+        _lib.check(L.gptst_affine1_bwd(_p(dy), _p(xm), _p(part), n, D, parts, _stream()), "gptst_affine1_bwd")
+        (tot,) = sum_partials(part)
+        return None, None, tot[0].view_as(weight), tot[1], None
+
+
+def masked_affine1(source, mask, weight, bias, fill):
+    """source (B,T,N,C) fp32 (channel 0 = flow), mask (B,T,N,1) int64 -> (B,T,N,D)."""
+    return _MaskedAffine1.apply(source, mask, weight, bias, fill)
+
+
 class _ProjOut(torch.autograd.Function):
     """y = x W^T + b for nn.Linear(D, O) with O <= 4 outputs (decoder.dim_flow_out, GPTST.py:454-458): one streaming pass over x
     forward, one backward (dX written, dW / db as per-CTA partials) instead of a GEMV and three library GEMM / reduce kernels."""

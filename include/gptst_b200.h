@@ -204,6 +204,10 @@ int gptst_score_head_bwd(const float* h, const float* W3, const float* prob, con
                          long rows, int D, int H, void* stream);
 int gptst_sum_partials(const float* const* ins, float* const* outs, const long* numel, const int* parts, int n, void* stream);
 int gptst_affine1_fwd(const float* x, const float* w, const float* b, float* y, long n, int D, void* stream);
+/* masked input embedding of the encoder, reference GPTST.py:419-421 (torch.where(mask == 0, scaler_zeros, mask * flow) followed by
+ * dim_in_flow): xm[i] = mask[i] == 0 ? fill : mask[i] * flow[i * flow_stride]; y[i][:] = xm[i] w[:] + b[:]; mask int64 (n,) */
+int gptst_masked_affine1_fwd(const float* flow, long flow_stride, const long long* mask, float fill, const float* w,
+                             const float* b, float* xm, float* y, long n, int D, void* stream);
 int gptst_affine1_bwd_parts(long n);
 int gptst_affine1_bwd(const float* dy, const float* x, float* part, long n, int D, int parts, void* stream);
 /* Sign-mask backward of gptst_gproj_fwd for D = 64 (csrc/gproj3.cu): dy = dY * act'(mask) with mask = 8 bytes per row of Y
