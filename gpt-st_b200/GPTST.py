@@ -13,8 +13,8 @@ parameters in the same order), same ``forward(source, label, batch_seen=None, ep
 Everything (B,T,N,*)-sized runs in libgptst_b200 kernels: the fused hyperTem blocks (csrc/htem_fused.cu), the cap chain, the
 scorer, the time-embedding MLPs and low-rank table generators (csrc/small_ops.cu), the mask construction (csrc/mask.cu: same
 ``rand_like`` / ``random.shuffle`` draws as the reference, so masks are bit-identical for equal seeds on the same device), the
-input / output projections and the loss.  PyTorch keeps the module tree, autograd bookkeeping, streams and a few elementwise
-glue ops ((1 - mask), the masked fill).
+input / output projections (the masked fill of the encoder input is part of its projection kernel) and the loss.  PyTorch keeps
+the module tree, autograd bookkeeping, streams and a few elementwise glue ops ((1 - mask), gradient accumulation of shared leaves).
 
 The model never touches ``'cuda:0'`` literally: it follows the device of its inputs, so one process per
 GPU (LOCAL_RANK) works for data parallel training.

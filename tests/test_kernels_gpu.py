@@ -534,3 +534,27 @@ def test_deferred_partial_sums_through_tables():
         assert_close(a, b.double().cpu(), atol=scale_tol(b, 1e-6), rtol=0.0, what="deferred partial sums")
 
 
+
+
+@pytest.mark.gpu
+def test_masked_affine1_matches_torch():
+    """where(mask == 0, fill, mask * flow) + nn.Linear(1, D) in one launch (reference GPTST.py:419-421): forward bit-exact
+    against the torch ops it replaces, dW / db against autograd."""
+    from gptst_b200 import ops
+    torch.manual_seed(3)
+    B, T, N, D, fill = 3, 12, 37, 64, -1.5767
+    src = torch.randn(B, T, N, 3, device="cuda")
+    mask = (torch.rand(B, T, N, 1, device="cuda") > 0.3).long()
+    lin = torch.nn.Linear(1, D).cuda()
+    w, b = lin.weight.detach().clone().requires_grad_(), lin.bias.detach().clone().requires_grad_()
+    y = ops.masked_affine1(src, mask, w, b, fill)
+    flow = src[..., 0:1]
+    masked = torch.where(mask == 0, torch.full_like(flow, fill), mask * flow)
+    w2, b2 = w.detach().clone().requires_grad_(), b.detach().clone().requires_grad_()
+    ref = torch.addcmul(b2, masked, w2.view(-1))                  # fmaf(x, w, b) per element, as the kernel computes it
+    assert torch.equal(y, ref)
+    g = torch.randn_like(y)
+    y.backward(g)
+    ref.backward(g)
+    assert_close(w.grad, w2.grad, atol=1e-5 * float(w2.grad.abs().max()), rtol=0.0, what="dW")
+    assert_close(b.grad, b2.grad, atol=1e-5 * float(b2.grad.abs().max()), rtol=0.0, what="db")
