@@ -386,22 +386,26 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
             int nks = (R - rbase + 15) / 16;
             nks = nks > NW ? NW : nks;
             for (int ks = 0; ks < nks; ++ks) {
+                uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
-                    const int id = warp + NW * i;
+                    // a warp's output tiles are CONSECUTIVE ids (mt = id >> 3 = 16-row block of dW, j = id & 7): they share the X^T
+                    // fragments of their row block, which are fetched once per row tile and block instead of once per output tile
+                    // (the kernel is bound by shared-memory wavefronts; profiles/ncu_route_fwd_r02.md)
+                    const int id = warp * TPW + i;
                     if (id < 32) {
-                        const int mt = id & 3, j = id >> 2;
-                        uint32_t ah[4], al[4] = {0u, 0u, 0u, 0u}, b0, b1, q0 = 0u, q1 = 0u;
-                        const uint32_t aaddr = smem_u32(Xs + (size_t)(16 * ks + 8 * (lane >> 4) + (lane & 7)) * ROWB +
-                                                        (16 * mt + 8 * ((lane >> 3) & 1)) * 2);
+                        const int mt = id >> 3, j = id & 7;
+                        uint32_t b0, b1, q0 = 0u, q1 = 0u;
+                        if (i == 0 || mt != ((id - 1) >> 3)) {
+                            const uint32_t aaddr = smem_u32(Xs + (size_t)(16 * ks + 8 * (lane >> 4) + (lane & 7)) * ROWB +
+                                                            (16 * mt + 8 * ((lane >> 3) & 1)) * 2);
+                            ldsm_x4_t(ah, aaddr);
+                            if (PREC == PREC_3XTF32) ldsm_x4_t(al, aaddr + LO);
+                        }
                         const uint32_t baddr =
                             smem_u32(Gs + (size_t)(16 * ks + 8 * ((lane >> 3) & 1) + (lane & 7)) * ROWB + (8 * j) * 2);
-                        ldsm_x4_t(ah, aaddr);
                         ldsm_x2_t(b0, b1, baddr);
-                        if (PREC == PREC_3XTF32) {
-                            ldsm_x4_t(al, aaddr + LO);
-                            ldsm_x2_t(q0, q1, baddr + LO);
-                        }
+                        if (PREC == PREC_3XTF32) ldsm_x2_t(q0, q1, baddr + LO);
                         mma3<PREC>(dwt[i], ah, al, b0, b1, q0, q1);
                     }
                 }
@@ -419,9 +423,9 @@ gproj2_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ Y, con
     float* dWo = dWp + ((size_t)split * G + grp) * D * D;
 #pragma unroll
     for (int i = 0; i < TPW; ++i) {
-        const int id = warp + NW * i;
+        const int id = warp * TPW + i;
         if (id < 32) {
-            const int mt = id & 3, j = id >> 2;
+            const int mt = id >> 3, j = id & 7;
             const int rin = 16 * mt + g, col = 8 * j + 2 * t;
             if (flags & 2) {
                 dWo[(size_t)col * D + rin] = dwm[i][0];       dWo[(size_t)(col + 1) * D + rin] = dwm[i][1];

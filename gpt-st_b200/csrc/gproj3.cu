@@ -269,22 +269,26 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
             nks = nks > NW ? NW : nks;
             for (int ks = 0; ks < nks; ++ks) {
                 const float un = tsc[ks];
+                uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                 for (int i = 0; i < TPW; ++i) {
-                    const int id = warp + NW * i;
+                    // a warp's output tiles are CONSECUTIVE ids (mt = id >> 3 = 16-row block of dW, j = id & 7): they share the X^T
+                    // fragments of their row block, which are fetched once per row tile and block instead of once per output tile
+                    // (the kernel is bound by shared-memory wavefronts; profiles/ncu_route_fwd_r02.md)
+                    const int id = warp * TPW + i;
                     if (id < 32) {
-                        const int mt = id & 3, j = id >> 2;
-                        uint32_t ah[4], al[4] = {0u, 0u, 0u, 0u}, b0, b1, q0 = 0u, q1 = 0u;
-                        const uint32_t aaddr = smem_u32(Xs + (size_t)(16 * ks + 8 * (lane >> 4) + (lane & 7)) * ROWB +
-                                                        (16 * mt + 8 * ((lane >> 3) & 1)) * 2);
+                        const int mt = id >> 3, j = id & 7;
+                        uint32_t b0, b1, q0 = 0u, q1 = 0u;
+                        if (i == 0 || mt != ((id - 1) >> 3)) {
+                            const uint32_t aaddr = smem_u32(Xs + (size_t)(16 * ks + 8 * (lane >> 4) + (lane & 7)) * ROWB +
+                                                            (16 * mt + 8 * ((lane >> 3) & 1)) * 2);
+                            ldsm_x4_t(ah, aaddr);
+                            if (PREC == PREC_3XTF32) ldsm_x4_t(al, aaddr + LO);
+                        }
                         const uint32_t baddr =
                             smem_u32(Gs + (size_t)(16 * ks + 8 * ((lane >> 3) & 1) + (lane & 7)) * ROWB + (8 * j) * 2);
-                        ldsm_x4_t(ah, aaddr);
                         ldsm_x2_t(b0, b1, baddr);
-                        if (PREC == PREC_3XTF32) {
-                            ldsm_x4_t(al, aaddr + LO);
-                            ldsm_x2_t(q0, q1, baddr + LO);
-                        }
+                        if (PREC == PREC_3XTF32) ldsm_x2_t(q0, q1, baddr + LO);
                         float t4[4] = {0.f, 0.f, 0.f, 0.f};
                         mma3<PREC>(t4, ah, al, b0, b1, q0, q1);
                         dwm[i][0] = fmaf(t4[0], un, dwm[i][0]); dwm[i][1] = fmaf(t4[1], un, dwm[i][1]);
@@ -299,9 +303,9 @@ gproj3_bwd_kernel(const float* __restrict__ dY, const uint2* __restrict__ Mask, 
     float* dWo = dWp + ((size_t)split * G + grp) * D * D;
 #pragma unroll
     for (int i = 0; i < TPW; ++i) {
-        const int id = warp + NW * i;
+        const int id = warp * TPW + i;
         if (id < 32) {
-            const int mt = id & 3, j = id >> 2;
+            const int mt = id >> 3, j = id & 7;
             const int rin = 16 * mt + g, col = 8 * j + 2 * t;
             if (flags & 2) {
                 dWo[(size_t)col * D + rin] = dwm[i][0];       dWo[(size_t)(col + 1) * D + rin] = dwm[i][1];
