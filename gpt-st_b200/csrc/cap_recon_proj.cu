@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(NTH, 2)
 cap_recon_proj_kernel(const float* __restrict__ c, const float* __restrict__ v, const float* __restrict__ x,
                       const uint4* __restrict__ wfrag, const float* __restrict__ bias, float* __restrict__ out,
                       float* __restrict__ recon, int BT, int N, int H) {
+    // (PDL: the wait sits behind the incidence staging below)
     constexpr int HP = (HMAX + 3) / 4 * 4;
     extern __shared__ __align__(128) unsigned char sm[];
     unsigned char* As = sm;                                              // [NG][ROWS][ROWB]
@@ -58,6 +59,10 @@ cap_recon_proj_kernel(const float* __restrict__ c, const float* __restrict__ v, 
 #pragma unroll
         for (int q = 0; q < HP / 4; ++q) dst[q] = make_float4(cv[4 * q], cv[4 * q + 1], cv[4 * q + 2], cv[4 * q + 3]);
     }
+    // c comes from the routing kernel, TWO launches back: complete once the hop kernel (the direct predecessor) let this grid
+    // start (pdl_enter waits before it triggers), so the tile above is staged while the hop kernel runs; v is the hop's output
+    pdl_wait();
+    pdl_trigger();
     __syncthreads();
 
     {   // build the 8 x 32 recon rows (A operands)
@@ -169,12 +174,12 @@ static int launch(const float* c, const float* v, const float* x, const void* wf
         auto k = cap_recon_proj_kernel<HMAX, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k<<<grid, NTH, smem, st>>>(c, v, x, (const uint4*)wfrag, bias, out, recon, BT, N, H);
+        launch_pdl(k, dim3(grid), dim3(NTH), smem, st, c, v, x, (const uint4*)wfrag, bias, out, recon, BT, N, H);
     } else {
         auto k = cap_recon_proj_kernel<HMAX, false>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        k<<<grid, NTH, smem, st>>>(c, v, x, (const uint4*)wfrag, bias, out, nullptr, BT, N, H);
+        launch_pdl(k, dim3(grid), dim3(NTH), smem, st, c, v, x, (const uint4*)wfrag, bias, out, (float*)nullptr, BT, N, H);
     }
     return (int)cudaGetLastError();
 }
@@ -200,6 +205,7 @@ __device__ __forceinline__ float4 addt(const float4& a, float t) { return make_f
 
 __global__ void __launch_bounds__(NT) cap_hop_ev_kernel(const float* __restrict__ s, const float* __restrict__ dyn,
                                                          float* __restrict__ e1, float* __restrict__ v, int T, int H, int HT) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char hsm[];
     const int K = T * H, b = blockIdx.x, tid = threadIdx.x;
     float4* Ss4 = reinterpret_cast<float4*>(hsm);                   // [K][16]  raw s of the sample
@@ -297,6 +303,6 @@ extern "C" int gptst_cap_hop_ev(const float* s, const float* dyn, float* e1, flo
     if (smem > 227 * 1024) return -2;
     cudaError_t e = cudaFuncSetAttribute(gptst::hop::cap_hop_ev_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    gptst::hop::cap_hop_ev_kernel<<<B, gptst::hop::NT, smem, (cudaStream_t)stream>>>(s, dyn, e1, v, T, H, HT);
+    gptst::launch_pdl(gptst::hop::cap_hop_ev_kernel, dim3(B), dim3(gptst::hop::NT), smem, (cudaStream_t)stream, s, dyn, e1, v, T, H, HT);
     return (int)cudaGetLastError();
 }

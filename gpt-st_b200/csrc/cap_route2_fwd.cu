@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bp,
                       const float* __restrict__ dadj, float* __restrict__ c_out, float* __restrict__ s_out,
                       float* __restrict__ z_out, int N, int H, int R, int ntiles) {
+    pdl_enter();
     extern __shared__ __align__(128) unsigned char smraw[];
     unsigned char* Prow = smraw;                                  // [ntiles*16][ROWB]
     unsigned char* Wt = Prow + (size_t)ntiles * 16 * ROWB;        // [64][ROWB]  (out o, permuted k), dead after Z
@@ -194,6 +195,7 @@ cap_route2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp,
     const float* xs = x + (size_t)slab * N * D;
 
     // ---- stage x (fp32 rows into the P slots), Wp (fp16 hi/lo, scaled, k permuted), bias; zero the v planes
+    // (staging Wp in front of the PDL wait was measured: the x copies then start later and the chain loses 4 us)
     for (int i = tid; i < ntiles * 16 * 16; i += NT) {
         const int r = i >> 4, ch = i & 15;
         unsigned char* dst = Prow + (size_t)r * ROWB + ch * 16;
@@ -382,7 +384,7 @@ static cudaError_t launch(const float* x, const float* Wp, const float* bp, cons
     auto kern = cap_route2_fwd_kernel<NW, TPW, MINB, PREC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<BT, NW * 32, smem, st>>>(x, Wp, bp, dadj, c, s, z, N, H, R, ntiles);
+    launch_pdl(kern, dim3(BT), dim3(NW * 32), smem, st, x, Wp, bp, dadj, c, s, z, N, H, R, ntiles);
     return cudaGetLastError();
 }
 

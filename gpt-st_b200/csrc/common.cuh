@@ -1,6 +1,7 @@
 // Shared device helpers for the GPT-ST sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 namespace gptst {
@@ -27,6 +28,22 @@ __device__ __forceinline__ float squash_df(float q) {
     // d/dq [ q / ((1+q)(r+eps)) ],  d(den)/dq = (r+eps) + (1+q)/(2r)
     float dden = re + (1.f + q) / (2.f * fmaxf(r, 1e-30f));
     return (den - q * dden) / (den * den);
+}
+
+// ---- programmatic dependent launch (PDL), FORWARD main chain only ---------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its stream predecessor still
+// runs; pdl_enter() as its first statement blocks until the predecessor has completed and its writes are visible (`wait`) and
+// THEN lets its own successor be scheduled (`launch_dependents`): a successor that starts early therefore knows that everything
+// older than its direct predecessor is complete, and may read such data before its own wait (cap_recon_proj stages the
+// incidence tile of the routing kernel while the hop kernel runs).  Nothing else of a kernel runs early: launch latency and CTA
+// scheduling overlap the predecessor.  No-ops without the attribute.  Measured (round 2): on EVERY
+// kernel of the step this costs 120 us -- in the backward the early CTAs take the tail-wave slots the low-priority side-stream
+// kernels live on (profiles/ab_pdl_slim_r02.md); the forward chain has no such tenants.  GPTST_B200_PDL=0 switches it off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_wait();
+    pdl_trigger();
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -170,6 +187,31 @@ __device__ __forceinline__ const float* cluster_map(const float* p, uint32_t ran
     uint64_t out;
     asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<uint64_t>(p)), "r"(rank));
     return reinterpret_cast<const float*>(out);
+}
+
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GPTST_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+// kern<<<grid, block, smem, st>>>(args...) with the programmatic-stream-serialization attribute (see pdl_enter)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace gptst

@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 htem_fwd_kernel(const __grid_constant__ CUtensorMap tm_eb, const __grid_constant__ CUtensorMap tm_mn,
                 const uint4* __restrict__ wfrag, const float* __restrict__ bias, float* __restrict__ out,
                 uint2* __restrict__ mask, float* __restrict__ ret, int N, int nch, int ntasks) {
+    pdl_enter();
     const int Npad = nch * NC;                          // mask rows are padded to whole 16-node chunks per (b, t)
     extern __shared__ __align__(128) unsigned char sm[];
     const float* land = reinterpret_cast<const float*>(sm + FwdSmem::land);
@@ -429,7 +430,7 @@ extern "C" int gptst_hypertem_fwd(const float* eb, const float* Mn, const void* 
     if (e != cudaSuccess) return (int)e;
     const int nch = (N + htf::NC - 1) / htf::NC, ntasks = B * nch;
     const int grid = htf::grid_for(ntasks, (const void*)htf::htem_fwd_kernel, htf::FwdSmem::total);
-    htf::htem_fwd_kernel<<<grid, htf::NTHREADS, htf::FwdSmem::total, (cudaStream_t)stream>>>(ta, tm, (const uint4*)wfrag, bias, out, (uint2*)mask,
+    launch_pdl(htf::htem_fwd_kernel, dim3(grid), dim3(htf::NTHREADS), (size_t)htf::FwdSmem::total, (cudaStream_t)stream, ta, tm, (const uint4*)wfrag, bias, out, (uint2*)mask,
                                                                                             ret, N, nch, ntasks);
     return (int)cudaGetLastError();
 }
