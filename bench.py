@@ -479,7 +479,7 @@ def run_ours(args):
             print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "e2e": value_e2e, "e2e_ms_per_step": ms_e2e / args.steps,
                               "last_loss": last_loss, "gpu_launches": launches, "clocks": clocks,
                               "env": {k: v for k, v in os.environ.items() if k.startswith("GPTST_B200_")}}), flush=True)
-            return 0
+    if rank == 0 and not args.no_rooflines:
         peak, peak_src = measured_peak()
         algo, cap_ms = cap_forward_roofline(N, D, B)
         ht_algo, ht_ms = hypertem_forward_time(N, D, B)
@@ -523,7 +523,11 @@ def run_ours(args):
         gc.collect()
         torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         sys.stdout.flush()
+        # a rank whose barrier kernel has finished must not tear its context down while a peer's is still reading its
+        # buffers over NVLink (observed: one rank exits, the other hangs in the barrier forever): give the peers a moment
+        time.sleep(3.0)
         os._exit(0)
     return 0
 

@@ -116,5 +116,8 @@ import gc
 gc.collect()
 torch.cuda.synchronize()
 dist.barrier()
+torch.cuda.synchronize()
 sys.stdout.flush()
+import time
+time.sleep(3.0)          # see bench.py: no rank tears its context down while a peer may still be inside the barrier
 os._exit(0 if (rank != 0 or ok) else 1)
