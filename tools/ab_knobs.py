@@ -8,9 +8,10 @@ import bench
 from gptst_b200.GPTST import GPTST_Model
 from gptst_b200.train import PretrainStep
 
-KNOBS = ("GPTST_B200_OPT_PREFETCH", "GPTST_B200_SCORER_PRIO", "GPTST_B200_EXPAND", "GPTST_B200_HTEM", "GPTST_B200_CAP")
-VARIANTS = [{}, {"GPTST_B200_OPT_PREFETCH": "1"}, {"GPTST_B200_SCORER_PRIO": "low"},
-            {"GPTST_B200_OPT_PREFETCH": "1", "GPTST_B200_SCORER_PRIO": "low"}, {"GPTST_B200_EXPAND": "native"}]
+# (library-side knobs such as GPTST_B200_PDL are read once per process by libgptst_b200.so: A/B those with separate bench.py runs)
+KNOBS = ("GPTST_B200_OPT_PREFETCH", "GPTST_B200_SCORER_PRIO", "GPTST_B200_HTEM", "GPTST_B200_CAP", "GPTST_B200_CAP_Z")
+VARIANTS = [{}, {"GPTST_B200_OPT_PREFETCH": "1"}, {"GPTST_B200_SCORER_PRIO": "low"}, {"GPTST_B200_CAP_Z": "recompute"},
+            {"GPTST_B200_HTEM": "split"}, {"GPTST_B200_CAP": "split"}]
 if len(sys.argv) > 1:          # python tools/ab_knobs.py '[{}, {"GPTST_B200_HTEM": "split"}]'
     VARIANTS = json.loads(sys.argv[1])
 N, D, B = bench.WORKLOADS["pems08"]

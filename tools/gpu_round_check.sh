@@ -8,7 +8,8 @@ T0=$(date +%s)
 el() { echo "[t+$(( $(date +%s) - T0 ))s] $*"; }
 # stand-alone C++ checks first: no Python start-up, a few seconds each (build them here: see the header of each .cu)
 [ -x tools/kbench ] && timeout 20 ./tools/kbench > $O/kbench.log 2>&1 && el "kbench: $(grep -c ' us ' $O/kbench.log) kernels timed"
-[ -x tools/gproj3_check ] && timeout 20 ./tools/gproj3_check > $O/gproj3_check.log 2>&1 && el "gproj3_check done"
+[ -x tools/htem_check ] && timeout 20 ./tools/htem_check > $O/htem_check.log 2>&1 && el "htem_check done"
+[ -x tools/cap_check ] && timeout 20 ./tools/cap_check > $O/cap_check.log 2>&1 && el "cap_check done"
 timeout 80 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | grep -v "Warning\|warnings.warn\|run_backward\|^$" | tail -30 > $O/pt_b.log
 el "pytest: $(tail -1 $O/pt_b.log)"
 timeout 70 python bench.py > $O/bench_v.json 2> $O/bench_v.err
@@ -20,7 +21,7 @@ timeout 90 ncu --metrics gpu__time_duration.sum --clock-control none --profile-f
 el "ncu list"
 timeout 25 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1
 el "smoke: $(tail -1 $O/smoke.log | cut -c1-120)"
-timeout 55 ncu --set full --clock-control none --import-source on -k regex:"gproj2_bwd|tmix_bwd" -s 22 -c 6 -f -o $O/prof_r01_bwd \
+timeout 55 ncu --set full --clock-control none --import-source on -k regex:"gproj2_bwd|htem_bwd" -s 22 -c 6 -f -o $O/prof_bwd \
     python tools/prof_blocks.py all > $O/ncu_bwd.log 2>&1
 el "ncu full"
 python - <<'PY'
