@@ -126,4 +126,6 @@ def check(rc: int, what: str) -> None:
         raise GptstLibraryError(f"{what}: NULL / empty argument")
     if rc == -2:
         raise GptstLibraryError(f"{what}: unsupported shape (D in {{64,128}}, T == 12, H <= 16, prec in {{1,3}})")
-    raise GptstLibraryError(f"{what}: CUDA error {rc}")
+    # cudaGetLastError() after the launch: a launch-configuration error of THIS call, or a sticky error left by an earlier
+    # asynchronous kernel of the process (run with CUDA_LAUNCH_BLOCKING=1 to attribute it)
+    raise GptstLibraryError(f"{what}: CUDA error {rc} (cudaGetLastError after the launch; may stem from an earlier asynchronous kernel)")
